@@ -1,0 +1,154 @@
+/*
+ * pokerl_b200.h -- C ABI of the B200-native batched No-Limit Texas Hold'em hot path.
+ *
+ * Drop-in boundary for sneppy/pokerl's Game.step / dealing / judger path.  The
+ * reference has no FFI of its own (it is pure Python + numpy); each entry point
+ * below names the reference interface it replaces (file:line relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success, < 0 on error; pkb_last_error() gives the text
+ *   - no exceptions cross the ABI; no torch types; device pointers are plain void*
+ *   - the handle owns the per-env device state; the caller owns action/output buffers
+ *   - all launches are ordered on the cudaStream_t passed as `stream` (void*, may be NULL)
+ *   - a handle is confined to one device and one host thread at a time
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ *
+ * Encodings (identical to the reference)
+ *   card value  = (suit << 4) | rank0, rank0 0=Ace,1=Two..12=King      cards.py:4-26
+ *   card id     = rank0 + 13*suit (bit index of 52-bit hand masks)      cards.py:22-26
+ *   player state FOLDED 0, ACTIVE 1, CALLED 2, ALL_IN 3, BROKEN 4       enums.py:130-134
+ *   move        FOLD 0, CHECK 1, CALL 2, RAISE_TEN 3, RAISE_QUARTER 4,
+ *               RAISE_HALF 5, ALL_IN 6                                   enums.py:104-111
+ *   hand rank   packed = (category << 20) | get_kickers_value(kickers)   judger.py:101-109
+ *               category 1 = straight flush .. 9 = high card, 10 = none  enums.py:9-18
+ */
+#ifndef POKERL_B200_H
+#define POKERL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PKB_ABI_VERSION 1
+#define PKB_MAX_PLAYERS 10
+#define PKB_NUM_MOVES 7
+
+/* step flag bits written to flags[env] */
+#define PKB_F_GAME_OVER 1u   /* Game.step()[0], game.py:565, 619 */
+#define PKB_F_HAND_OVER 2u   /* Game.step()[1] */
+#define PKB_F_ROUND_OVER 4u  /* Game.step()[2] */
+#define PKB_F_INVALID 64u    /* action not in valid_actions: env untouched (ValueError at game.py:649-651) */
+#define PKB_F_POISONED 128u  /* reference would not terminate (game.py:607) or would assert (game.py:473) */
+
+#define PKB_NEXT_TURN_CAP 64 /* next_turn() calls allowed inside one step before PKB_F_POISONED */
+
+typedef struct pkb_env pkb_env; /* opaque handle: N lockstep Game objects on one GPU */
+
+/* Game(**config), game.py:242-264.  start_credits: one value per seat (game.py:247, 408). */
+typedef struct pkb_config {
+    uint32_t abi_version;     /* PKB_ABI_VERSION */
+    int32_t device;           /* CUDA device ordinal */
+    uint64_t num_envs;        /* N local environments */
+    uint64_t env_id_base;     /* global id of local env 0 (multi-GPU sharding); global ids must be < 2^32 */
+    int32_t num_players;      /* 2..PKB_MAX_PLAYERS                                  game.py:246 */
+    int32_t dealer;           /* reset(dealer=...), default 0                        game.py:403 */
+    double start_credits[PKB_MAX_PLAYERS]; /*                                        game.py:247 */
+    double big_blind;         /*                                                     game.py:248 */
+    double small_blind;       /*                                                     game.py:249 */
+    uint64_t seed;            /* Philox key; replaces the global MT19937 of game.py:424 */
+    int32_t auto_reset;       /* 1: reset() an env inside the step that ends its game */
+    int32_t reserved;
+} pkb_config;
+
+/* Device pointers into the handle's state, for zero-copy wrapping (torch / cupy / raw CUDA).
+ * f64 planes are [num_players][stride] (seat-major, env fastest); the rest are [stride]. */
+typedef struct pkb_state_view {
+    uint64_t num_envs;
+    uint64_t stride;          /* elements between consecutive seats (num_envs rounded up to the tile) */
+    int32_t num_players;
+    int32_t reserved;
+    double *credits;          /* Game.credits                 game.py:260 */
+    double *bets;             /* Game.bets                    game.py:261 */
+    double *pending_bets;     /* Game.pending_bets            game.py:262 */
+    double *payoffs;          /* Game.payoffs                 game.py:264 */
+    double *minimum_raise_value; /* Game.minimum_raise_value  game.py:263 */
+    uint8_t *player_states;   /* Game.player_states [P][stride] game.py:259 */
+    uint32_t *meta;           /* turn | dealer<<3 | small_blind_idx<<8 | big_blind_idx<<13 | active_player<<18 */
+    uint32_t *hand;           /* Game.hand                    game.py:255 */
+    uint32_t *episode;        /* number of reset() calls seen by the env (Philox counter word) */
+} pkb_state_view;
+
+/* Aggregate counters kept on the device (pkb_stats). */
+typedef struct pkb_stats_t {
+    uint64_t steps;           /* valid env-steps executed */
+    uint64_t hands;           /* end_hand() calls (game.py:453) */
+    uint64_t showdowns;       /* end_hand() calls that ranked hands (game.py:483-528) */
+    uint64_t games;           /* steps that returned game_over */
+    uint64_t invalid;         /* steps rejected as invalid */
+    uint64_t poisoned;        /* steps that hit the loop cap / the reference's assert */
+    double payoff_sum[PKB_MAX_PLAYERS]; /* sum over hands of Game.payoffs per seat */
+} pkb_stats_t;
+
+const char *pkb_last_error(void);
+int pkb_abi_version(void);
+/* number of CUDA devices visible; < 0 if the runtime cannot initialise */
+int pkb_device_count(void);
+
+/* ---- Game: game.py ------------------------------------------------------------ */
+int pkb_create(const pkb_config *cfg, pkb_env **out);                     /* Game.__init__  game.py:242 */
+int pkb_destroy(pkb_env *h);
+/* Game.reset, game.py:397-412.  env_mask: device u8[N], nonzero = reset that env; NULL = all. */
+int pkb_reset(pkb_env *h, const uint8_t *env_mask, void *stream);
+/* Game.step, game.py:621-700 on every env.  actions: device i32[N].  flags/valid: device u8[N] out
+ * (valid = bit a set iff move a is valid for the NEW active player, game.py:339-383); either may be NULL. */
+int pkb_step(pkb_env *h, const int32_t *actions, uint8_t *flags, uint8_t *valid, void *stream);
+/* Same, with the action drawn on device: weighted choice over the valid mask from
+ * Philox(seed, env_id, step_idx) (RandomAgent, agents/random.py:16-17 when weights == NULL).
+ * weights: host u32[7] or NULL.  actions_out: device i32[N] or NULL (the actions taken, for replay). */
+int pkb_step_random(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int32_t *actions_out, uint8_t *flags,
+                    uint8_t *valid, void *stream);
+/* Sampler alone (K5): actions for the CURRENT state, without stepping. */
+int pkb_sample_actions(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int32_t *actions_out, void *stream);
+/* Game.get_valid_actions(player), game.py:339-383.  player < 0: each env's active player. */
+int pkb_valid_actions(pkb_env *h, int32_t player, uint8_t *valid, void *stream);
+/* Game.game_over, game.py:316-320: device u8[N]. */
+int pkb_game_over(pkb_env *h, uint8_t *out, void *stream);
+int pkb_state(pkb_env *h, pkb_state_view *out);
+/* Current deal of every env, device u8 [5+2P][stride]: rows 0..4 board (game.py:278),
+ * rows 5+2p, 6+2p hole cards of seat p (game.py:385-389); card values. */
+int pkb_cards(pkb_env *h, uint8_t *out, void *stream);
+/* Observation features for q_learning.py:29-33: packed eval_hand(player_hand) of `player`
+ * (< 0: active player) on 2/5/6/7 cards depending on the street.  out: device u32[N]. */
+int pkb_hand_features(pkb_env *h, int32_t player, uint32_t *out, void *stream);
+int pkb_stats(pkb_env *h, pkb_stats_t *out, void *stream);     /* synchronises the stream */
+int pkb_stats_reset(pkb_env *h, void *stream);
+
+/* ---- dealing: replaces random.shuffle(self.deck), game.py:424 ------------------ */
+/* Host-side replay of one deal: out[5+2P] card values.  Pure function of its arguments. */
+int pkb_deal(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t hand, int32_t num_players, uint8_t *out);
+
+/* ---- judger: judger.py --------------------------------------------------------- */
+/* eval_hand on n hands of k cards each (0 <= k <= 7), judger.py:7-99.  cards: device u8[n][k]
+ * card values (duplicates allowed, as in the reference's own tests).  out: device u32[n] packed. */
+int pkb_eval_cards(const uint8_t *cards, int32_t k, uint64_t n, uint32_t *out, void *stream);
+/* eval_hand on n hands given as 52-bit id masks (<= 7 bits set).  masks: device u64[n]. */
+int pkb_eval_masks(const uint64_t *masks, uint64_t n, uint32_t *out, void *stream);
+/* All C(52,k) hands (k = 1..7), enumerated on device in colex order of the id mask.
+ * hist: host u64[11] by category; sums: host u64[2] = {sum packed, sum packed*(mask % 1000003)} mod 2^64;
+ * out: device u32[count] or NULL (packed of hands first..first+count-1). */
+int pkb_eval_exhaustive(int32_t k, uint64_t first, uint64_t count, uint64_t *hist, uint64_t *sums, uint32_t *out,
+                        void *stream);
+/* n random 7-card hands from Philox(seed, index): writes masks (device u64[n], may be NULL). */
+int pkb_random_hands(uint64_t seed, uint64_t n, uint64_t *masks, void *stream);
+/* compare_rankings, judger.py:111-158, on n tables of p packed rankings each.
+ * packed: device u32[n][p]; onehot: device u8[n][p]. */
+int pkb_compare_rankings(const uint32_t *packed, int32_t p, uint64_t n, uint8_t *onehot, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+// pkb_eval.cuh -- branch-light bitmask hand evaluator, bug-compatible with the reference judger.
+//
+// Replaces eval_hand / get_kickers_value / compare_rankings (reference judger.py:7-158).
+// Input is a 52-bit mask over card ids (id = rank0 + 13*suit, cards.py:22-26) with <= 7 bits set;
+// output is packed = (category << 20) | kickers, first kicker in the most significant nibble
+// (judger.py:101-109).  Lower category is better, then larger kicker value.
+//
+// The reference scans two sorted copies of the hand (judger.py:38-80).  For hands without
+// duplicate cards that scan equals a standard evaluator except for three behaviours, all
+// reproduced here (verified exhaustively for 1..7 cards against the oracle):
+//   X   = the suit holding >= 5 cards if there is one, else the lowest-numbered suit present
+//         (the suit-ordered scan freezes on a 5-card suit, judger.py:58, else ends on the last suit)
+//   run = the LOWEST maximal run of consecutive ranks inside X (the straight-flush tracker
+//         restarts on every gap and never freezes, judger.py:56-57)
+//   (1) a straight flush counts only if `run` itself has >= 5 cards (judger.py:90)
+//   (2) A-5-4-3-2 by rank with no six returns STRAIGHT[5] before flush is considered,
+//       unless run is exactly 5-4-3-2 (judger.py:86-88)
+//   (3) if run is exactly 5-4-3-2 and X has no ace, the wheel check is skipped (judger.py:83-85)
+// Hands WITH duplicate cards (the reference's own tests use them) go through eval_cards_literal.
+#pragma once
+#include "pkb_common.cuh"
+
+namespace pkb {
+
+// append the k highest ranks of x (bit i = rank i+1) as nibbles below v
+PKB_HD uint32_t pack_top(uint32_t x, int k, uint32_t v)
+{
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        if (i < k && x) {
+            const int h = topbit32(x);
+            v = (v << 4) | (uint32_t)(h + 1);
+            x ^= 1u << h;
+        }
+    }
+    return v;
+}
+
+// 13-bit suit slice of the id mask (bit 0 = ace) -> rank order (bit 0 = two .. bit 12 = ace), cards.py:8-14
+PKB_HD uint32_t suit_ranks(uint64_t m, int suit)
+{
+    const uint32_t x = (uint32_t)(m >> (13 * suit)) & 0x1fffu;
+    return (x >> 1) | ((x & 1u) << 12);
+}
+
+PKB_HD uint32_t eval_mask52(uint64_t m)
+{
+    if (m == 0) return PACKED_NONE;  // judger.py:30
+    const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
+    const uint32_t any = s0 | s1 | s2 | s3;
+
+    // suit X and its lowest maximal run
+    const uint32_t fl = popc32(s0) >= 5 ? s0 : popc32(s1) >= 5 ? s1 : popc32(s2) >= 5 ? s2 : popc32(s3) >= 5 ? s3 : 0u;
+    const uint32_t sx = fl ? fl : s0 ? s0 : s1 ? s1 : s2 ? s2 : s3;
+    const uint32_t run = sx & ~(sx + (sx & (0u - sx)));
+
+    const uint32_t st5 = any & (any << 1) & (any << 2) & (any << 3) & (any << 4);  // bit i: ranks i-3..i+1 all present
+    if (run == 0xFu) {                                                              // judger.py:83-85
+        if (sx & 0x1000u) return (HR_STRAIGHT_FLUSH << 20) | 4u;
+    } else if (st5 == 0 && (any & 0x1000u) && (any & ~(any + (any & (0u - any)))) == 0xFu)  // judger.py:86-88
+        return (HR_STRAIGHT << 20) | 4u;
+
+    if (popc32(run) >= 5) return (HR_STRAIGHT_FLUSH << 20) | (uint32_t)(topbit32(run) + 1);  // judger.py:90
+
+    // rank multiplicities, bit-sliced
+    const uint32_t a01 = s0 & s1, x01 = s0 ^ s1, a23 = s2 & s3, x23 = s2 ^ s3;
+    const uint32_t quad = a01 & a23;
+    const uint32_t trip = (a01 & x23) | (x01 & a23);
+    const uint32_t pair = (a01 & ~(s2 | s3)) | (a23 & ~(s0 | s1)) | (x01 & x23);
+
+    if (quad) {  // judger.py:91
+        const int q = topbit32(quad);
+        return (HR_POKER << 20) | pack_top(any & ~(1u << q), 1, (uint32_t)(q + 1));
+    }
+    int t = 0;
+    if (trip) {
+        t = topbit32(trip);
+        const uint32_t trip2 = trip ^ (1u << t);
+        if (trip2) return (HR_FULL << 20) | ((uint32_t)(t + 1) << 4) | (uint32_t)(topbit32(trip2) + 1);  // :92
+        if (pair) return (HR_FULL << 20) | ((uint32_t)(t + 1) << 4) | (uint32_t)(topbit32(pair) + 1);    // :93
+    }
+    if (fl) return (HR_FLUSH << 20) | pack_top(fl, 5, 0);                                   // :94
+    if (st5) return (HR_STRAIGHT << 20) | (uint32_t)(topbit32(st5) + 1);                    // :95
+    if (trip) return (HR_TRIS << 20) | pack_top(any & ~(1u << t), 2, (uint32_t)(t + 1));    // :96
+    if (pair) {
+        const int p1 = topbit32(pair);
+        const uint32_t pair2 = pair ^ (1u << p1);
+        if (pair2) {  // :97
+            const int p2 = topbit32(pair2);
+            return (HR_TWO_PAIR << 20) |
+                   pack_top(any & ~(1u << p1) & ~(1u << p2), 1, ((uint32_t)(p1 + 1) << 4) | (uint32_t)(p2 + 1));
+        }
+        return (HR_PAIR << 20) | pack_top(any & ~(1u << p1), 3, (uint32_t)(p1 + 1));  // :98
+    }
+    return (HR_HIGH << 20) | pack_top(any, 5, 0);  // :99
+}
+
+// ---- list form (duplicates allowed): the two-sorted-copies scan of judger.py:38-99 ----------------
+
+PKB_HD int cv_rank(uint32_t v) { const int r = (int)(v & 0xfu); return r ? r : 13; }
+PKB_HD int cv_suit(uint32_t v) { return (int)(v >> 4); }
+
+PKB_HD uint32_t eval_cards_literal(const uint8_t* cards, int n)
+{
+    if (n <= 0) return PACKED_NONE;
+    if (n > 7) n = 7;
+    // keys: by-rank (rank only) and by-suit ((suit << 4) | rank); both sorted descending.
+    // Order among equal keys cannot change the result: the rank scan reads ranks only, and equal
+    // suit keys are identical cards.
+    int kr[7], ks[7];
+    for (int i = 0; i < n; ++i) {
+        const int r = cv_rank(cards[i]), k = (cv_suit(cards[i]) << 4) | r;
+        int j = i;
+        while (j > 0 && kr[j - 1] < r) { kr[j] = kr[j - 1]; --j; }
+        kr[j] = r;
+        j = i;
+        while (j > 0 && ks[j - 1] < k) { ks[j] = ks[j - 1]; --j; }
+        ks[j] = k;
+    }
+    if (n == 1) return (HR_HIGH << 20) | (uint32_t)kr[0];  // :31
+    if (n == 2)                                            // :32-35
+        return kr[0] == kr[1] ? (HR_PAIR << 20) | (uint32_t)kr[0]
+                              : (HR_HIGH << 20) | ((uint32_t)kr[0] << 4) | (uint32_t)kr[1];
+
+    // flush tracker: suit, count, first index; straight-flush tracker: start rank, length
+    int f_suit = -1, f_cnt = 0, f_start = 0, b_top = 0, b_len = 0, b_suit = -1;
+    // n-of-a-kind groups in descending rank order; straight tracker
+    int g_rank = 0, g_cnt = 0, s_top = 0, s_len = 0;
+    int quad1 = 0, trip1 = 0, trip2 = 0, pair1 = 0, pair2 = 0;
+    for (int i = 0; i <= n; ++i) {
+        if (i < n) {
+            const int sr = ks[i] & 0xf, ss = ks[i] >> 4;
+            if (ss == f_suit) {  // :52-57
+                ++f_cnt;
+                if (sr + b_len == b_top) ++b_len;
+                else { b_top = sr; b_len = 1; b_suit = ss; }
+            } else if (f_cnt < 5) {  // :58
+                f_suit = b_suit = ss; f_cnt = b_len = 1; b_top = sr; f_start = i;
+            }
+        }
+        const int r = i < n ? kr[i] : -1;
+        if (r == g_rank) ++g_cnt;  // :61
+        else {                     // :62-72 and the flush of the last group, :77-80
+            if (g_cnt == 4) { if (!quad1) quad1 = g_rank; }
+            else if (g_cnt == 3) { if (!trip1) trip1 = g_rank; else if (!trip2) trip2 = g_rank; }
+            else if (g_cnt == 2) { if (!pair1) pair1 = g_rank; else if (!pair2) pair2 = g_rank; }
+            if (i < n) {
+                g_rank = r; g_cnt = 1;
+                if (r + s_len == s_top) ++s_len;
+                else if (s_len < 5) { s_top = r; s_len = 1; }
+            }
+        }
+    }
+    if (b_len == 4 && b_top == 4) {  // :83-85
+        for (int i = 0; i < n; ++i)
+            if (ks[i] == ((b_suit << 4) | 13)) return (HR_STRAIGHT_FLUSH << 20) | 4u;
+    } else if (s_len == 4 && s_top == 4) {  // :86-88
+        if (kr[0] == 13) return (HR_STRAIGHT << 20) | 4u;
+    }
+    uint32_t v = 0;
+    int nk = 0;
+    if (b_len >= 5) return (HR_STRAIGHT_FLUSH << 20) | (uint32_t)b_top;  // :90
+    if (quad1) {                                                          // :91
+        v = (uint32_t)quad1;
+        for (int i = 0; i < n && nk < 1; ++i)
+            if (kr[i] != quad1) { v = (v << 4) | (uint32_t)kr[i]; ++nk; }
+        return (HR_POKER << 20) | v;
+    }
+    if (trip2) return (HR_FULL << 20) | ((uint32_t)trip1 << 4) | (uint32_t)trip2;            // :92
+    if (trip1 && pair1) return (HR_FULL << 20) | ((uint32_t)trip1 << 4) | (uint32_t)pair1;   // :93
+    if (f_cnt >= 5) {                                                                        // :94
+        for (int i = f_start; i < n && nk < 5; ++i, ++nk) v = (v << 4) | (uint32_t)(ks[i] & 0xf);
+        return (HR_FLUSH << 20) | v;
+    }
+    if (s_len >= 5) return (HR_STRAIGHT << 20) | (uint32_t)s_top;  // :95
+    if (trip1) {                                                   // :96
+        v = (uint32_t)trip1;
+        for (int i = 0; i < n && nk < 2; ++i)
+            if (kr[i] != trip1) { v = (v << 4) | (uint32_t)kr[i]; ++nk; }
+        return (HR_TRIS << 20) | v;
+    }
+    if (pair2) {  // :97
+        v = ((uint32_t)pair1 << 4) | (uint32_t)pair2;
+        for (int i = 0; i < n && nk < 1; ++i)
+            if (kr[i] != pair1 && kr[i] != pair2) { v = (v << 4) | (uint32_t)kr[i]; ++nk; }
+        return (HR_TWO_PAIR << 20) | v;
+    }
+    if (pair1) {  // :98
+        v = (uint32_t)pair1;
+        for (int i = 0; i < n && nk < 3; ++i)
+            if (kr[i] != pair1) { v = (v << 4) | (uint32_t)kr[i]; ++nk; }
+        return (HR_PAIR << 20) | v;
+    }
+    for (int i = 0; i < n && nk < 5; ++i, ++nk) v = (v << 4) | (uint32_t)kr[i];  // :99
+    return (HR_HIGH << 20) | v;
+}
+
+// eval_hand on a card list: the mask path when the cards are distinct, the literal scan otherwise
+PKB_HD uint32_t eval_cards(const uint8_t* cards, int n)
+{
+    uint64_t m = 0;
+    for (int i = 0; i < n && i < 7; ++i) m |= 1ull << card_id_from_value(cards[i]);
+    if (popc64(m) == n) return eval_mask52(m);
+    return eval_cards_literal(cards, n);
+}
+
+// compare_rankings, judger.py:133-158, as a running scan state.  Line 148 assigns
+// `kicker = best_kicker` instead of raising best_kicker, so a later, better kicker replaces the
+// winner list but leaves the bar where the FIRST hand of the best category put it.
+struct WinnerScan {
+    uint32_t best_rank, best_kicker, winners;  // winners: bit per seat
+    PKB_HDM WinnerScan() : best_rank(HR_NONE), best_kicker(0), winners(0) {}
+    PKB_HDM void feed(int idx, uint32_t packed)
+    {
+        const uint32_t rank = packed >> 20, kicker = packed & 0xfffffu;
+        if (rank < best_rank) { best_rank = rank; best_kicker = kicker; winners = 1u << idx; }
+        else if (rank == best_rank) {
+            if (kicker > best_kicker) winners = 1u << idx;
+            else if (kicker == best_kicker) winners |= 1u << idx;
+        }
+    }
+};
+
+}  // namespace pkb

@@ -1,0 +1,101 @@
+// pkb_philox.cuh -- counter-based dealing and action sampling (Philox4x32-10).
+//
+// Replaces random.shuffle(self.deck) (reference game.py:424, CPython's global MT19937) with a
+// pure function of (seed, env_id, episode, hand): any env's deck can be regenerated anywhere --
+// at showdown inside the step kernel, for observations, or on the host to replay the hand into
+// the reference Game.  Decks are therefore never stored in HBM.
+//
+// Deal spec: draw i of a hand (i = 0 .. 4+2P) takes 32-bit word (i & 3) of the Philox block with
+// counter {env_id, hand, episode, i >> 2} and key {seed_lo, seed_hi}; j = mulhi32(word, 52 - i)
+// selects the j-th smallest card id not drawn yet.  Draws 0..4 are the board (game.py:278),
+// draws 5+2p, 6+2p the hole cards of seat p (game.py:385-389).
+//
+// Action spec: counter {env_id, step_idx, 0, 0x80000000}, word 0; t = mulhi32(word, W) with
+// W = total weight of the valid moves; the move is the first valid one whose cumulative
+// weight exceeds t (uniform weights = RandomAgent, agents/random.py:16-17).
+#pragma once
+#include "pkb_common.cuh"
+
+namespace pkb {
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+PKB_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// position of the j-th (0-based) set bit of a 52-bit mask; j < popcount(f)
+PKB_HD uint32_t select_bit(uint64_t f, uint32_t j)
+{
+    uint32_t w = (uint32_t)f, pos = 0;
+    uint32_t c = (uint32_t)popc32(w);
+    if (j >= c) { j -= c; w = (uint32_t)(f >> 32); pos = 32; }
+    c = (uint32_t)popc32(w & 0xffffu);
+    if (j >= c) { j -= c; w >>= 16; pos += 16; }
+    c = (uint32_t)popc32(w & 0xffu);
+    if (j >= c) { j -= c; w >>= 8; pos += 8; }
+    c = (uint32_t)popc32(w & 0xfu);
+    if (j >= c) { j -= c; w >>= 4; pos += 4; }
+    c = (uint32_t)popc32(w & 0x3u);
+    if (j >= c) { j -= c; w >>= 2; pos += 2; }
+    c = w & 1u;
+    if (j >= c) pos += 1;
+    return pos;
+}
+
+// Sequential dealer: call next() 5+2P times; ids are card ids (0..51).
+struct Dealer {
+    uint32_t k0, k1, env, hand, episode;
+    uint64_t free_mask;
+    U4 blk;
+    int i;
+    PKB_HDM Dealer(uint64_t seed, uint32_t env_id, uint32_t episode_, uint32_t hand_)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), env(env_id), hand(hand_), episode(episode_),
+          free_mask((1ull << 52) - 1), blk{0, 0, 0, 0}, i(0)
+    {
+    }
+    PKB_HDM uint32_t next()
+    {
+        const int lane = i & 3;
+        if (lane == 0) blk = philox4x32_10(U4{env, hand, episode, (uint32_t)(i >> 2)}, k0, k1);
+        const uint32_t word = lane == 0 ? blk.x : lane == 1 ? blk.y : lane == 2 ? blk.z : blk.w;
+        const uint32_t id = select_bit(free_mask, mulhi32(word, (uint32_t)(52 - i)));
+        free_mask &= ~(1ull << id);
+        ++i;
+        return id;
+    }
+};
+
+// weights == nullptr -> uniform
+PKB_HD int sample_action(uint64_t seed, uint32_t env_id, uint32_t step_idx, uint32_t valid_mask, const uint32_t* weights)
+{
+    const U4 r = philox4x32_10(U4{env_id, step_idx, 0u, 0x80000000u}, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t total = 0;
+#pragma unroll
+    for (int a = 0; a < NUM_MOVES; ++a)
+        if (valid_mask >> a & 1u) total += weights ? weights[a] : 1u;
+    const uint32_t t = mulhi32(r.x, total);
+    uint32_t acc = 0;
+    int pick = MV_FOLD;
+    bool found = false;
+#pragma unroll
+    for (int a = 0; a < NUM_MOVES; ++a)
+        if (valid_mask >> a & 1u) {
+            acc += weights ? weights[a] : 1u;
+            if (!found && acc > t) { pick = a; found = true; }
+        }
+    return pick;
+}
+
+}  // namespace pkb

@@ -1,0 +1,59 @@
+// hostcheck.cpp -- compiles the PRODUCT's host/device headers (pokerl_b200/csrc/*.cuh) for the host so
+// the CPU test-suite can check their algorithms against the oracle without a GPU.  Test-only: the
+// product never loads this library, and the GPU tests check the same functions through the C ABI.
+#include <stddef.h>
+#include <stdint.h>
+
+#include "pkb_eval.cuh"
+#include "pkb_philox.cuh"
+
+extern "C" {
+
+uint32_t hc_eval_mask(uint64_t m) { return pkb::eval_mask52(m); }
+uint32_t hc_eval_cards(const uint8_t* c, int n) { return pkb::eval_cards(c, n); }
+uint32_t hc_eval_cards_literal(const uint8_t* c, int n) { return pkb::eval_cards_literal(c, n); }
+
+void hc_eval_masks(const uint64_t* m, size_t n, uint32_t* out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = pkb::eval_mask52(m[i]);
+}
+
+static uint64_t next_same_popcount(uint64_t v)
+{
+    uint64_t c = v & -v, r = v + c;
+    return (((r ^ v) >> 2) / c) | r;
+}
+
+// all C(52,k) masks in increasing order starting from the lowest; hist/sums as pkb_eval_exhaustive
+void hc_eval_exhaustive(int k, uint64_t* hist, uint64_t* sums, uint32_t* out, uint64_t count)
+{
+    uint64_t m = (1ull << k) - 1;
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint32_t p = pkb::eval_mask52(m);
+        hist[p >> 20]++;
+        sums[0] += p;
+        sums[1] += (uint64_t)p * (m % 1000003ull);
+        if (out) out[i] = p;
+        m = next_same_popcount(m);
+    }
+}
+
+void hc_deal(uint64_t seed, uint32_t env, uint32_t episode, uint32_t hand, int P, uint8_t* out)
+{
+    pkb::Dealer d(seed, env, episode, hand);
+    for (int i = 0; i < 5 + 2 * P; ++i) out[i] = (uint8_t)pkb::card_value_from_id(d.next());
+}
+
+int hc_sample(uint64_t seed, uint32_t env, uint32_t step, uint32_t valid, const uint32_t* w)
+{
+    return pkb::sample_action(seed, env, step, valid, w);
+}
+
+int hc_compare(const uint32_t* packed, int n, uint8_t* onehot)
+{
+    pkb::WinnerScan ws;
+    for (int i = 0; i < n; ++i) ws.feed(i, packed[i]);
+    for (int i = 0; i < n; ++i) onehot[i] = (ws.winners >> i) & 1u;
+    return pkb::popc32(ws.winners);
+}
+}
