@@ -103,6 +103,8 @@ int pkb_create(const pkb_config *cfg, pkb_env **out);                     /* Gam
 int pkb_destroy(pkb_env *h);
 /* Game.reset, game.py:397-412.  env_mask: device u8[N], nonzero = reset that env; NULL = all. */
 int pkb_reset(pkb_env *h, const uint8_t *env_mask, void *stream);
+/* The `dealer` keyword of Game.reset(dealer=...), game.py:403: used by every later reset (and auto-reset). */
+int pkb_set_reset_dealer(pkb_env *h, int32_t dealer);
 /* Game.step, game.py:621-700 on every env.  actions: device i32[N].  flags/valid: device u8[N] out
  * (valid = bit a set iff move a is valid for the NEW active player, game.py:339-383); either may be NULL. */
 int pkb_step(pkb_env *h, const int32_t *actions, uint8_t *flags, uint8_t *valid, void *stream);

@@ -1,0 +1,219 @@
+"""GameBatch: N lockstep reference `Game` tables on one B200, driven through the C ABI.
+
+This is the thin host layer between the pokerl-compatible facade (game.py, envs/) and
+libpokerl_b200.so.  PyTorch is used only for device buffers, streams and (multi-GPU)
+torch.distributed; all game logic runs in the hand-written CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+class _DeviceArray:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, address, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(address), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner  # keeps the pkb handle alive as long as the tensor lives
+
+
+def _credits_vector(num_players, start_credits):
+    """start_credits as the reference accepts it (game.py:247, 408): int, list or ndarray."""
+    if isinstance(start_credits, (int, np.integer)) and not isinstance(start_credits, bool):
+        return [float(start_credits)] * num_players
+    if isinstance(start_credits, float):
+        # the reference does `100.0[:]` here -> TypeError
+        raise TypeError("'float' object is not subscriptable")
+    vec = [float(x) for x in start_credits]
+    if len(vec) != num_players:
+        raise ValueError(f"could not broadcast start_credits of length {len(vec)} to {num_players} players")
+    return vec
+
+
+class _Handle:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        if self.ptr:
+            try:
+                nat.lib().pkb_destroy(self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+
+class GameBatch:
+    """N environments on one device.  All tensors returned are views of, or live on, that device."""
+
+    def __init__(self, num_envs, num_players=4, start_credits=100, big_blind=2, small_blind=1, dealer=0, seed=0,
+                 env_id_base=0, auto_reset=False, device=None):
+        nat.require_cuda()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.num_envs = int(num_envs)
+        self.num_players = int(num_players)
+        if not 2 <= self.num_players <= nat.MAX_PLAYERS:
+            raise ValueError(f"num_players must be in 2..{nat.MAX_PLAYERS} (got {num_players})")
+        cfg = nat.PkbConfig()
+        cfg.abi_version = nat.ABI_VERSION
+        cfg.device = self.device.index
+        cfg.num_envs = self.num_envs
+        cfg.env_id_base = int(env_id_base)
+        cfg.num_players = self.num_players
+        cfg.dealer = int(dealer)
+        for p, x in enumerate(_credits_vector(self.num_players, start_credits)):
+            cfg.start_credits[p] = x
+        cfg.big_blind = float(big_blind)
+        cfg.small_blind = float(small_blind)
+        cfg.seed = int(seed) & (2 ** 64 - 1)
+        cfg.auto_reset = int(bool(auto_reset))
+        self.config = cfg
+        self.seed, self.env_id_base = cfg.seed, int(env_id_base)
+        h = C.c_void_p()
+        nat.check(nat.lib().pkb_create(C.byref(cfg), C.byref(h)))
+        self._h = _Handle(h)
+        self._wrap_state()
+        with torch.cuda.device(self.device):
+            self.flags = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self.valid = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self.actions_taken = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+
+    # ---- zero-copy state ---------------------------------------------------------------------
+    def _wrap_state(self):
+        sv = nat.PkbStateView()
+        nat.check(nat.lib().pkb_state(self._h.ptr, C.byref(sv)))
+        P, S, N = self.num_players, int(sv.stride), self.num_envs
+        self.stride = S
+
+        def wrap(addr, shape, typestr):
+            return torch.as_tensor(_DeviceArray(addr, shape, typestr, self._h), device=self.device)
+
+        # [P, N] views of the seat-major planes (env index fastest in memory)
+        self.credits = wrap(sv.credits, (P, S), "<f8")[:, :N]
+        self.bets = wrap(sv.bets, (P, S), "<f8")[:, :N]
+        self.pending_bets = wrap(sv.pending_bets, (P, S), "<f8")[:, :N]
+        self.payoffs = wrap(sv.payoffs, (P, S), "<f8")[:, :N]
+        self.minimum_raise_value = wrap(sv.minimum_raise_value, (S,), "<f8")[:N]
+        self.player_states = wrap(sv.player_states, (P, S), "|u1")[:, :N]
+        self._meta = wrap(sv.meta, (S,), "<i4")[:N]
+        self._hand = wrap(sv.hand, (S,), "<i4")[:N]
+        self._episode = wrap(sv.episode, (S,), "<i4")[:N]
+
+    @property
+    def turn(self):
+        return self._meta & 7
+
+    @property
+    def dealer_idx(self):
+        return (self._meta >> 3) & 31
+
+    @property
+    def small_blind_idx(self):
+        return (self._meta >> 8) & 31
+
+    @property
+    def big_blind_idx(self):
+        return (self._meta >> 13) & 31
+
+    @property
+    def active_player(self):
+        return (self._meta >> 18) & 31
+
+    @property
+    def hand(self):
+        return self._hand
+
+    @property
+    def episode(self):
+        return self._episode
+
+    # ---- calls -------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def set_reset_dealer(self, dealer: int):
+        """The `dealer` keyword of Game.reset (game.py:403) for every later reset."""
+        nat.check(nat.lib().pkb_set_reset_dealer(self._h.ptr, int(dealer)))
+        self.config.dealer = int(dealer)
+
+    def reset(self, env_mask=None):
+        """Game.reset() on every env, or on those where env_mask (uint8/bool [N]) is nonzero."""
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        nat.check(nat.lib().pkb_reset(self._h.ptr, nat.ptr(env_mask), self._stream()))
+
+    def step(self, actions, flags=None, valid=None):
+        """Game.step(actions[i]) on env i.  actions: int32 [N] on this device.  Returns (flags, valid)."""
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        flags = self.flags if flags is None else flags
+        valid = self.valid if valid is None else valid
+        nat.check(nat.lib().pkb_step(self._h.ptr, nat.ptr(actions), nat.ptr(flags), nat.ptr(valid), self._stream()))
+        return flags, valid
+
+    def step_random(self, step_idx, weights=None, record_actions=False, flags=None, valid=None):
+        """One step with the on-device random agent (uniform, or integer `weights` per move)."""
+        w = None if weights is None else (C.c_uint32 * nat.NUM_MOVES)(*[int(x) for x in weights])
+        flags = self.flags if flags is None else flags
+        valid = self.valid if valid is None else valid
+        out = self.actions_taken if record_actions else None
+        nat.check(nat.lib().pkb_step_random(self._h.ptr, int(step_idx) & 0xFFFFFFFF, w, nat.ptr(out), nat.ptr(flags),
+                                            nat.ptr(valid), self._stream()))
+        return flags, valid
+
+    def sample_actions(self, step_idx, weights=None, out=None):
+        w = None if weights is None else (C.c_uint32 * nat.NUM_MOVES)(*[int(x) for x in weights])
+        out = self.actions_taken if out is None else out
+        nat.check(nat.lib().pkb_sample_actions(self._h.ptr, int(step_idx) & 0xFFFFFFFF, w, nat.ptr(out), self._stream()))
+        return out
+
+    def valid_actions(self, player=-1, out=None):
+        """Bit mask of valid moves (game.py:339-383) for `player` (-1: each env's active player)."""
+        out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device) if out is None else out
+        nat.check(nat.lib().pkb_valid_actions(self._h.ptr, int(player), nat.ptr(out), self._stream()))
+        return out
+
+    def game_over(self, out=None):
+        out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device) if out is None else out
+        nat.check(nat.lib().pkb_game_over(self._h.ptr, nat.ptr(out), self._stream()))
+        return out
+
+    def cards(self):
+        """Current deal, uint8 [5+2P, N] card values: rows 0..4 board, 5+2p/6+2p hole cards of seat p."""
+        rows = 5 + 2 * self.num_players
+        buf = torch.empty((rows, self.stride), dtype=torch.uint8, device=self.device)
+        nat.check(nat.lib().pkb_cards(self._h.ptr, nat.ptr(buf), self._stream()))
+        return buf[:, :self.num_envs]
+
+    def hand_features(self, player=-1, out=None):
+        """packed eval_hand(player_hand) per env (uint32 stored as int64-safe int32 bits)."""
+        out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device) if out is None else out
+        nat.check(nat.lib().pkb_hand_features(self._h.ptr, int(player), nat.ptr(out), self._stream()))
+        return out
+
+    def stats(self) -> dict:
+        s = nat.PkbStats()
+        nat.check(nat.lib().pkb_stats(self._h.ptr, C.byref(s), self._stream()))
+        return dict(steps=s.steps, hands=s.hands, showdowns=s.showdowns, games=s.games, invalid=s.invalid,
+                    poisoned=s.poisoned, payoff_sum=[s.payoff_sum[p] for p in range(self.num_players)])
+
+    def stats_reset(self):
+        nat.check(nat.lib().pkb_stats_reset(self._h.ptr, self._stream()))
+
+    # ---- host snapshots (tests, scalar facade) -----------------------------------------------
+    def export(self) -> dict:
+        """Host copy of the whole state in the oracle's export layout ([P, N] planes, [N] vectors)."""
+        meta = self._meta.cpu().numpy().astype(np.int64)
+        return dict(
+            credits=self.credits.cpu().numpy(), bets=self.bets.cpu().numpy(), pending=self.pending_bets.cpu().numpy(),
+            payoffs=self.payoffs.cpu().numpy(), states=self.player_states.cpu().numpy(),
+            minraise=self.minimum_raise_value.cpu().numpy(), turn=(meta & 7).astype(np.int32),
+            dealer=((meta >> 3) & 31).astype(np.int32), sb=((meta >> 8) & 31).astype(np.int32),
+            bb=((meta >> 13) & 31).astype(np.int32), active=((meta >> 18) & 31).astype(np.int32),
+            hand=self._hand.cpu().numpy().astype(np.int32), episode=self._episode.cpu().numpy().astype(np.uint32))
