@@ -102,7 +102,7 @@ def lib():
     """The loaded shared library; built on first use when nvcc is available, otherwise an error."""
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("PKB_LIB") or _build.LIB  # PKB_LIB: load an experimental build instead
         if not os.path.exists(path):
             try:
                 _build.build_native()

@@ -323,15 +323,16 @@ PKB_D void step_begin(V& v, size_t s, Meta& m, Ctl& c, int action, uint32_t vmas
 
 // Game.end_hand, first part (game.py:453-482): commit, count the potential winners, settle a
 // last-stand pot.  Returns true when the hand needs the ranked showdown (game.py:483-528).
+// From here until setup_hand the PENDING plane carries self.payoffs (it is all zero after commit and
+// is rewritten by the next setup_hand), so no per-seat register array crosses a phase boundary.
 template <int P, class V>
-PKB_D bool end_hand_begin(V& v, size_t s, Ctl& c, double (&pay)[P])
+PKB_D bool end_hand_begin(V& v, size_t s, Ctl& c)
 {
     const size_t ld = v.ld();
-    commit<P>(v, s);  // :457-461
+    commit<P>(v, s);  // :457-461; pending (= payoffs from here on) is now 0.0, :468
     int n = 0, first = -1;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        pay[p] = 0.0;  // :468
         const int st = v.st[p * ld + s];
         if (st != ST_BROKEN && st != ST_FOLDED) {  // :471
             if (first < 0) first = p;
@@ -345,24 +346,22 @@ PKB_D bool end_hand_begin(V& v, size_t s, Ctl& c, double (&pay)[P])
     }
     if (n == 1) {  // :475-482
         const double pot = sum_plane<P>(v, v.bt, s);
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-            if (p == first) {
-                pay[p] = pot;
-                v.cr[p * ld + s] += pot;
-            }
+        v.pd[first * ld + s] = pot;
+        v.cr[first * ld + s] += pot;
         return false;
     }
     return true;
 }
 
-// Game.end_hand, ranked showdown (game.py:483-528).  The working copy of bets lives in the
-// pending plane, which is all zero between commit and the next setup_hand.
-template <int P, class V>
-PKB_D void showdown(V& v, size_t s, Ctl& c, double (&pay)[P], uint64_t seed, uint32_t env_id, uint32_t episode)
+// Game.end_hand, ranked showdown (game.py:483-528).  `rank7(mask)` evaluates a 7-card id mask
+// (eval_mask52, possibly out of line).  The working copy of bets is kept in registers; payoffs
+// are written to the pending plane at the end.
+template <int P, class V, class Rank7>
+PKB_D void showdown(V& v, size_t s, const Ctl& c, uint64_t seed, uint32_t env_id, uint32_t episode, Rank7 rank7)
 {
     const size_t ld = v.ld();
     uint32_t rk[P];
+    double b[P], pay[P];
     uint32_t todo = 0;
     {  // :488-489 eval_hand(board + hole) for CALLED / ALL_IN seats, NONE for the others
         Dealer d(seed, env_id, episode, v.hand[s]);
@@ -374,9 +373,10 @@ PKB_D void showdown(V& v, size_t s, Ctl& c, double (&pay)[P], uint64_t seed, uin
             const uint64_t hole = (1ull << d.next()) | (1ull << d.next());
             const int st = v.st[p * ld + s];
             const bool shows = st == ST_CALLED || st == ST_ALL_IN;
-            rk[p] = shows ? eval_mask52(board | hole) : PACKED_NONE;
+            rk[p] = shows ? rank7(board | hole) : PACKED_NONE;
             todo |= (uint32_t)shows << p;
-            v.pd[p * ld + s] = v.bt[p * ld + s];  // :485 working copy
+            b[p] = v.bt[p * ld + s];  // :485 working copy
+            pay[p] = 0.0;
         }
     }
     int n = c.npw;
@@ -390,13 +390,9 @@ PKB_D void showdown(V& v, size_t s, Ctl& c, double (&pay)[P], uint64_t seed, uin
             if ((todo >> i & 1u) && (!have || x < least)) { p = i; least = x; have = true; }
         }
         todo &= ~(1u << p);
-        double b[P];
         bool nothing_left = true;
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-            b[i] = v.pd[i * ld + s];
-            nothing_left &= b[i] <= 0.0;
-        }
+        for (int i = 0; i < P; ++i) nothing_left &= b[i] <= 0.0;
         if (nothing_left) break;  // :499
         if (n == 1) {             // :500-505
             const double rest = np_sum<P>(b);
@@ -431,29 +427,34 @@ PKB_D void showdown(V& v, size_t s, Ctl& c, double (&pay)[P], uint64_t seed, uin
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            if (i == p) rk[i] = PACKED_NONE;          // :522
-            v.pd[i * ld + s] = b[i] - layer[i];       // :523
+            if (i == p) rk[i] = PACKED_NONE;  // :522
+            b[i] = b[i] - layer[i];           // :523
         }
         --n;  // :525
     }
 #pragma unroll
-    for (int p = 0; p < P; ++p) v.cr[p * ld + s] += pay[p];  // :528
+    for (int p = 0; p < P; ++p) {
+        v.cr[p * ld + s] += pay[p];  // :528
+        v.pd[p * ld + s] = pay[p];
+    }
 }
 
 // Game.end_hand, last part (game.py:530-539), then what the caller of end_hand does with its
-// return value (game.py:565 / 609-611 or game.py:619).
-template <int P, class V>
-PKB_D void end_hand_finish(V& v, size_t s, Meta& m, Ctl& c, double (&pay)[P], double* payoffs_out, size_t out_ld,
-                           size_t out_idx, const GameConst& gc)
+// return value (game.py:565 / 609-611 or game.py:619).  `deal(m)` runs setup_hand (possibly out of
+// line) and returns the new Meta; `pay_out` receives the hand's final payoffs.
+template <int P, class V, class Deal>
+PKB_D void end_hand_finish(V& v, size_t s, Meta& m, Ctl& c, double* payoffs_out, size_t out_ld, size_t out_idx,
+                           double (&pay_out)[P], Deal deal)
 {
     const size_t ld = v.ld();
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        pay[p] -= v.bt[p * ld + s];                                   // :531
-        payoffs_out[p * out_ld + out_idx] = pay[p];
-        if (v.cr[p * ld + s] <= 0.0) v.st[p * ld + s] = ST_BROKEN;   // :536
+        const double pay = v.pd[p * ld + s] - v.bt[p * ld + s];  // :531
+        pay_out[p] = pay;
+        payoffs_out[p * out_ld + out_idx] = pay;
+        if (v.cr[p * ld + s] <= 0.0) v.st[p * ld + s] = ST_BROKEN;  // :536
     }
-    setup_hand<P>(v, s, m, gc);  // :539 -- runs even when the game is over
+    m = deal(m);  // :539 setup_hand -- runs even when the game is over
     const int over = game_over<P>(v, s) ? (int)F_GAME_OVER : 0;
     if (c.cont) {  // next_turn: `return self.game_over, True, True`, then the scan goes on (:609-611)
         c.done = over | (int)(F_HAND_OVER | F_ROUND_OVER);

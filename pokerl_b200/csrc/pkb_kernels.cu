@@ -46,13 +46,25 @@ struct StepArgs {
     uint32_t weights[NUM_MOVES];
 };
 
-constexpr int TILE = 256;
+constexpr int TILE = 256;   // env-count granularity of the HBM planes (stride is a multiple of it)
+constexpr int SLOTS = 96;   // per-warp shared-memory slots: 32 staging + 32 end-hand + 32 showdown
+constexpr int STEP_WARPS = 4;  // warps per block of the step kernel (each warp is autonomous)
 
 template <int P>
-constexpr size_t tile_smem_bytes()
+__host__ __device__ constexpr size_t warp_smem_bytes();
+
+// resident blocks per SM the step kernel is compiled for: what 227 KB of shared memory allow, at most 7
+template <int P>
+__host__ __device__ constexpr int step_min_blocks()
 {
-    // f64 planes (3P+1), meta/hand/ctl u32, two u16 slot lists, P state bytes
-    return (size_t)TILE * ((3 * P + 1) * 8 + 3 * 4 + 2 * 2 + P);
+    constexpr size_t per_block = warp_smem_bytes<P>() * STEP_WARPS + 1024;
+    constexpr int by_smem = (int)((size_t)232448 / per_block);
+#ifdef PKB_STEP_MAX_BLOCKS  // tuning knob for experiments
+    constexpr int cap = PKB_STEP_MAX_BLOCKS;
+#else
+    constexpr int cap = 7;
+#endif
+    return by_smem > cap ? cap : (by_smem < 1 ? 1 : by_smem);
 }
 
 PKB_D View<0> global_view(const DevState& d)
@@ -60,74 +72,300 @@ PKB_D View<0> global_view(const DevState& d)
     return View<0>{d.cr, d.bt, d.pd, d.mr, d.st, d.meta, d.hand, (size_t)d.stride};
 }
 
-// block-wide compaction of the slots whose control word asks for phase `want`
-PKB_D void compact_slots(const uint32_t* ctl, uint32_t want, uint16_t* list, int* counter)
+// The warp's shared-memory slots plus the control words kept beside the game state, and the
+// warp's statistics accumulators (written by lane 0 only)
+template <int P>
+struct WarpSlots {
+    View<SLOTS> v;
+    uint32_t* ctl;       // automaton control word (pkb_game.cuh, struct Ctl)
+    uint32_t* env;       // local env index of the slot's occupant
+    uint32_t* wstat;     // [STAT_COUNT] per-warp counters
+    double* wpay;        // [P] per-warp payoff sums
+};
+
+template <int P>
+__host__ __device__ constexpr size_t warp_smem_bytes()
 {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const bool mine = (ctl[tid] & 3u) == want;
-    const unsigned vote = __ballot_sync(0xffffffffu, mine);
-    int base = 0;
-    if (lane == 0 && vote) base = atomicAdd(counter, __popc(vote));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (mine) list[base + __popc(vote & ((1u << lane) - 1u))] = (uint16_t)tid;
+    // per slot: f64 planes (3P+1), meta/hand/ctl/env u32, P state bytes; then P f64 + 8 u32 of statistics
+    return (size_t)SLOTS * ((3 * P + 1) * 8 + 4 * 4 + P) + (size_t)P * 8 + 32;
 }
 
-// --------------------------------------------------------------------------------------------
-// K1/K2: Game.step (game.py:621-700) for one tile of TILE envs per block
-// --------------------------------------------------------------------------------------------
-template <int P, bool SAMPLE>
-__global__ void __launch_bounds__(TILE) step_kernel(const __grid_constant__ StepArgs a)
+template <int P>
+PKB_D WarpSlots<P> carve_slots(unsigned char* base)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* f64 = reinterpret_cast<double*>(smem_raw);
-    View<TILE> v;
-    v.cr = f64;
-    v.bt = f64 + P * TILE;
-    v.pd = f64 + 2 * P * TILE;
-    v.mr = f64 + 3 * P * TILE;
-    uint32_t* u32 = reinterpret_cast<uint32_t*>(f64 + (3 * P + 1) * TILE);
-    v.meta = u32;
-    v.hand = u32 + TILE;
-    uint32_t* ctl = u32 + 2 * TILE;
-    uint16_t* list_e = reinterpret_cast<uint16_t*>(u32 + 3 * TILE);
-    uint16_t* list_s = list_e + TILE;
-    v.st = reinterpret_cast<uint8_t*>(list_s + TILE);
-    v.ld_rt = TILE;
-    __shared__ int s_count[2];
-    __shared__ unsigned long long s_stats[STAT_COUNT];
-    __shared__ double s_paysum[MAX_PLAYERS];
+    WarpSlots<P> w;
+    double* f64 = reinterpret_cast<double*>(base);
+    w.v.cr = f64;
+    w.v.bt = f64 + P * SLOTS;
+    w.v.pd = f64 + 2 * P * SLOTS;
+    w.v.mr = f64 + 3 * P * SLOTS;
+    w.wpay = f64 + (3 * P + 1) * SLOTS;
+    uint32_t* u32 = reinterpret_cast<uint32_t*>(f64 + (3 * P + 1) * SLOTS + P);
+    w.v.meta = u32;
+    w.v.hand = u32 + SLOTS;
+    w.ctl = u32 + 2 * SLOTS;
+    w.env = u32 + 3 * SLOTS;
+    w.wstat = u32 + 4 * SLOTS;
+    w.v.st = reinterpret_cast<uint8_t*>(u32 + 4 * SLOTS + 8);
+    w.v.ld_rt = SLOTS;
+    return w;
+}
 
-    const DevState& d = a.d;
-    const int tid = threadIdx.x;
-    const size_t tile0 = (size_t)blockIdx.x * TILE;
-    const size_t env = tile0 + tid;
-    const bool live = env < d.n;
+// warp-level event counter: lane 0 adds the number of lanes for which `event` holds
+PKB_D void count_event(uint32_t* counter, bool event)
+{
+    const unsigned vote = __ballot_sync(0xffffffffu, event);
+    if (vote && (threadIdx.x & 31) == 0) *counter += (uint32_t)__popc(vote);
+}
 
-    // ---- stage the tile: HBM planes -> shared memory (stride is a multiple of TILE, so every
-    //      lane's address is in bounds; padding lanes are inert)
+template <int P>
+PKB_D void move_slot(WarpSlots<P>& w, int from, int to)
+{
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        v.cr[p * TILE + tid] = d.cr[p * d.stride + env];
-        v.bt[p * TILE + tid] = d.bt[p * d.stride + env];
-        v.pd[p * TILE + tid] = d.pd[p * d.stride + env];
-        v.st[p * TILE + tid] = d.st[p * d.stride + env];
+        w.v.cr[p * SLOTS + to] = w.v.cr[p * SLOTS + from];
+        w.v.bt[p * SLOTS + to] = w.v.bt[p * SLOTS + from];
+        w.v.pd[p * SLOTS + to] = w.v.pd[p * SLOTS + from];
+        w.v.st[p * SLOTS + to] = w.v.st[p * SLOTS + from];
     }
-    v.mr[tid] = d.mr[env];
-    v.meta[tid] = d.meta[env];
-    v.hand[tid] = d.hand[env];
-    if (tid < STAT_COUNT) s_stats[tid] = 0;
-    if (tid < MAX_PLAYERS) s_paysum[tid] = 0.0;
+    w.v.mr[to] = w.v.mr[from];
+    w.v.meta[to] = w.v.meta[from];
+    w.v.hand[to] = w.v.hand[from];
+    w.ctl[to] = w.ctl[from];
+    w.env[to] = w.env[from];
+}
 
-    // ---- phase A, one thread per env: validate, bet, scan seats up to the first end_hand
-    uint32_t n_hands = 0, n_showdowns = 0;
+// ---- out-of-line pieces: ONE copy each in the kernel image.  The step kernel's warps run
+//      different phases at the same time, so its code must stay small enough for the SM's
+//      instruction cache; everything below takes and returns plain words.
+__device__ __noinline__ uint32_t rank7_call(uint64_t mask) { return eval_mask52(mask); }
+
+template <int P>
+__device__ __noinline__ uint32_t setup_hand_call(unsigned char* warp_base, int slot, uint32_t meta_word, const GameConst& gc)
+{
+    WarpSlots<P> w = carve_slots<P>(warp_base);
+    Meta m = unpack_meta(meta_word);
+    setup_hand<P>(w.v, slot, m, gc);
+    return pack_meta(m);
+}
+
+template <int P>
+__device__ __noinline__ void showdown_call(unsigned char* warp_base, int slot, uint32_t ctl_word, uint64_t seed,
+                                           uint32_t env_id, uint32_t episode)
+{
+    WarpSlots<P> w = carve_slots<P>(warp_base);
+    showdown<P>(w.v, slot, unpack_ctl(ctl_word), seed, env_id, episode, [](uint64_t m) { return rank7_call(m); });
+}
+
+// Step epilogue for one finished env: flags, valid mask of the new active player, state back to HBM.
+// Warp-uniform call; `active` selects the lanes that retire their slot.
+template <int P>
+PKB_D void retire_slot(WarpSlots<P>& w, int slot, bool active, const StepArgs& a)
+{
+    const DevState& d = a.d;
+    Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
+    if (active) c = unpack_ctl(w.ctl[slot]);
+    const uint32_t f = (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
+    if (a.gc.track_stats) {
+        count_event(&w.wstat[STAT_STEPS], active && !c.invalid);
+        count_event(&w.wstat[STAT_GAMES], active && (f & F_GAME_OVER));
+        count_event(&w.wstat[STAT_INVALID], active && c.invalid);
+        count_event(&w.wstat[STAT_POISONED], active && c.poisoned);
+    }
+    if (!active) return;
+    const size_t env = w.env[slot];
+    if (a.flags) a.flags[env] = (uint8_t)f;
+    if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(w.v, slot, unpack_meta(w.v.meta[slot]).act);
+    if (c.invalid) return;  // nothing changed (game.py:649-651 raises before any mutation)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        d.cr[p * d.stride + env] = w.v.cr[p * SLOTS + slot];
+        d.bt[p * d.stride + env] = w.v.bt[p * SLOTS + slot];
+        d.pd[p * d.stride + env] = w.v.pd[p * SLOTS + slot];
+        d.st[p * d.stride + env] = w.v.st[p * SLOTS + slot];
+    }
+    d.mr[env] = w.v.mr[slot];
+    d.meta[env] = w.v.meta[slot];
+    d.hand[env] = w.v.hand[slot];
+}
+
+// What follows Game.end_hand once the payoffs are in the pending plane: finish the hand, deal the next
+// one, resume the seat scan -- and any further hand that ends inside the same step (rare: all-in blinds
+// make whole hands play themselves) -- then auto-reset if asked.  Warp-uniform, out of line.
+// `ctl_word` must have pc == PC_END_HAND semantics already resolved by end_hand_begin (+ showdown);
+// `asserted`: end_hand_begin found no potential winner (game.py:473 would raise AssertionError).
+template <int P>
+__device__ __noinline__ uint32_t finish_hand_call(unsigned char* warp_base, int slot, uint32_t ctl_word, bool active,
+                                                  bool asserted, const StepArgs& a)
+{
+    WarpSlots<P> w = carve_slots<P>(warp_base);
+    const DevState& d = a.d;
+    Ctl c = unpack_ctl(ctl_word);
     double paysum[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) paysum[p] = 0.0;
-    {
+    uint32_t more_hands = 0, more_shows = 0;
+    if (active) {
+        Meta m = unpack_meta(w.v.meta[slot]);
+        const size_t env = w.env[slot];
+        const auto deal = [&](const Meta& mm) { return unpack_meta(setup_hand_call<P>(warp_base, slot, pack_meta(mm), a.gc)); };
+        while (!asserted) {
+            double pay[P];
+            end_hand_finish<P>(w.v, slot, m, c, d.payoffs, d.stride, env, pay, deal);
+#pragma unroll
+            for (int p = 0; p < P; ++p) paysum[p] += pay[p];
+            if (c.pc != PC_END_HAND) break;
+            ++more_hands;  // another hand ended inside this step
+            if (end_hand_begin<P>(w.v, slot, c)) {
+                ++more_shows;
+                showdown_call<P>(warp_base, slot, pack_ctl(c), a.gc.seed, a.gc.env_id_base + (uint32_t)env, d.episode[env]);
+            } else if (c.poisoned)
+                asserted = true;
+        }
+        if (asserted) {  // payoffs were zeroed at game.py:468 before the assert
+#pragma unroll
+            for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
+            c.done = c.cont ? (int)((game_over<P>(w.v, slot) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER)
+                            : (int)F_HAND_OVER;
+            c.pc = PC_DONE;
+        } else if ((c.done & (int)F_GAME_OVER) && !c.poisoned && a.gc.auto_reset) {
+            // Game.reset() right after the step that ended the game (game.py:397-412)
+            d.episode[env] += 1;
+            m.dealer = a.gc.dealer;
+            m.act = 0;
+            w.v.hand[slot] = 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                w.v.cr[p * SLOTS + slot] = a.gc.start_credits[p];
+                w.v.st[p * SLOTS + slot] = ST_ACTIVE;
+            }
+            m = deal(m);
+        }
+        w.v.meta[slot] = pack_meta(m);
+    }
+    if (a.gc.track_stats) {
+        const uint32_t h = __reduce_add_sync(0xffffffffu, more_hands), sh = __reduce_add_sync(0xffffffffu, more_shows);
+        if ((threadIdx.x & 31) == 0) {
+            w.wstat[STAT_HANDS] += h;
+            w.wstat[STAT_SHOWDOWNS] += sh;
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            double x = paysum[p];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0) w.wpay[p] += x;
+        }
+    }
+    return pack_ctl(c);
+}
+
+// Ranked showdowns of the warp's showdown buffer (slots 64..64+count), one env per lane
+template <int P>
+__device__ __noinline__ void flush_showdowns(unsigned char* warp_base, int s_count, const StepArgs& a)
+{
+    WarpSlots<P> w = carve_slots<P>(warp_base);
+    const int lane = threadIdx.x & 31, slot = 64 + lane;
+    const bool active = lane < s_count;
+    __syncwarp();
+    uint32_t ctl_word = 0;
+    if (active) {
+        ctl_word = w.ctl[slot];
+        const size_t env = w.env[slot];
+        showdown_call<P>(warp_base, slot, ctl_word, a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.d.episode[env]);
+    }
+    if (a.gc.track_stats) count_event(&w.wstat[STAT_SHOWDOWNS], active);
+    ctl_word = finish_hand_call<P>(warp_base, slot, ctl_word, active, false, a);
+    if (active) w.ctl[slot] = ctl_word;
+    retire_slot<P>(w, slot, active, a);
+    __syncwarp();
+}
+
+// end_hand for the warp's end-hand buffer (slots 32..32+count): last-stand hands finish here,
+// ranked hands move on to the showdown buffer.  Returns the new fill of the showdown buffer.
+template <int P>
+__device__ __noinline__ int flush_end_hands(unsigned char* warp_base, int e_count, int s_count, const StepArgs& a)
+{
+    WarpSlots<P> w = carve_slots<P>(warp_base);
+    const int lane = threadIdx.x & 31, slot = 32 + lane;
+    const bool active = lane < e_count;
+    __syncwarp();
+    bool ranked = false;
+    uint32_t ctl_word = 0;
+    bool asserted = false;
+    if (active) {
+        Ctl c = unpack_ctl(w.ctl[slot]);
+        ranked = end_hand_begin<P>(w.v, slot, c);
+        asserted = !ranked && c.poisoned;
+        if (ranked) c.pc = PC_SHOWDOWN;
+        ctl_word = pack_ctl(c);
+        w.ctl[slot] = ctl_word;
+    }
+    if (a.gc.track_stats) count_event(&w.wstat[STAT_HANDS], active);
+    ctl_word = finish_hand_call<P>(warp_base, slot, ctl_word, active && !ranked, asserted, a);
+    if (active && !ranked) w.ctl[slot] = ctl_word;
+    retire_slot<P>(w, slot, active && !ranked, a);
+    const unsigned vote = __ballot_sync(0xffffffffu, ranked);
+    const int k = __popc(vote);
+    if (k) {
+        if (s_count + k > 32) {
+            flush_showdowns<P>(warp_base, s_count, a);
+            s_count = 0;
+        }
+        __syncwarp();
+        if (ranked) move_slot<P>(w, slot, 64 + s_count + __popc(vote & ((1u << lane) - 1u)));
+        s_count += k;
+        if (s_count == 32) {
+            flush_showdowns<P>(warp_base, s_count, a);
+            s_count = 0;
+        }
+    }
+    __syncwarp();
+    return s_count;
+}
+
+// --------------------------------------------------------------------------------------------
+// K1/K2: Game.step (game.py:621-700).  Persistent grid; every warp owns 96 shared-memory slots
+// and walks 32-env sub-tiles on its own: phase A (validate, bet, scan seats) runs one env per lane
+// on the staging slots; envs whose hand ends are parked in the warp's end-hand buffer and those
+// that need ranking in its showdown buffer, and each buffer is processed when it fills, so the
+// expensive branches run at (nearly) full warp width without any block-level barrier.
+// --------------------------------------------------------------------------------------------
+template <int P, bool SAMPLE>
+__global__ void __launch_bounds__(STEP_WARPS * 32, step_min_blocks<P>()) step_kernel(const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char* warp_base = smem_raw + (size_t)wib * warp_smem_bytes<P>();
+    WarpSlots<P> w = carve_slots<P>(warp_base);
+    const DevState& d = a.d;
+    if (lane < 8) w.wstat[lane] = 0;
+    if (lane < P) w.wpay[lane] = 0.0;
+    int e_count = 0, s_count = 0;  // warp-uniform fill of the end-hand / showdown buffers
+    __syncwarp();
+
+    const size_t n_sub = d.stride / 32, total_warps = (size_t)gridDim.x * STEP_WARPS;
+    for (size_t sub = (size_t)blockIdx.x * STEP_WARPS + wib; sub < n_sub; sub += total_warps) {
+        const size_t env = sub * 32 + lane;
+        const bool live = env < d.n;
+        // ---- stage 32 envs: HBM planes -> staging slots (slot = lane; 256 B per plane row)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            w.v.cr[p * SLOTS + lane] = d.cr[p * d.stride + env];
+            w.v.bt[p * SLOTS + lane] = d.bt[p * d.stride + env];
+            w.v.pd[p * SLOTS + lane] = d.pd[p * d.stride + env];
+            w.v.st[p * SLOTS + lane] = d.st[p * d.stride + env];
+        }
+        w.v.mr[lane] = d.mr[env];
+        w.v.meta[lane] = d.meta[env];
+        w.v.hand[lane] = d.hand[env];
+        w.env[lane] = (uint32_t)env;
+
+        // ---- phase A: validate the action, bet, scan seats up to the first end_hand
         Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
         if (live) {
-            Meta m = unpack_meta(v.meta[tid]);
-            const uint32_t vm = valid_mask<P>(v, tid, m.act);
+            Meta m = unpack_meta(w.v.meta[lane]);
+            const uint32_t vm = valid_mask<P>(w.v, lane, m.act);
             int action;
             if (SAMPLE) {
                 action = sample_action(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx, vm,
@@ -135,108 +373,40 @@ __global__ void __launch_bounds__(TILE) step_kernel(const __grid_constant__ Step
                 if (a.actions_out) a.actions_out[env] = action;
             } else
                 action = a.actions[env];
-            step_begin<P>(v, tid, m, c, action, vm, a.gc);
-            v.meta[tid] = pack_meta(m);
+            step_begin<P>(w.v, lane, m, c, action, vm, a.gc);
+            w.v.meta[lane] = pack_meta(m);
         }
-        ctl[tid] = pack_ctl(c);
-    }
+        w.ctl[lane] = pack_ctl(c);
+        retire_slot<P>(w, lane, live && c.pc == PC_DONE, a);
 
-    // ---- phases B/C on compacted slot lists: end_hand, then the ranked showdown
-    for (;;) {
-        if (tid < 2) s_count[tid] = 0;
-        __syncthreads();
-        compact_slots(ctl, PC_END_HAND, list_e, &s_count[0]);
-        __syncthreads();
-        const int n_e = s_count[0];
-        if (n_e == 0) break;
-        if (tid < n_e) {
-            const int s = list_e[tid];
-            Ctl c = unpack_ctl(ctl[s]);
-            Meta m = unpack_meta(v.meta[s]);
-            double pay[P];
-            ++n_hands;
-            if (end_hand_begin<P>(v, s, c, pay)) c.pc = PC_SHOWDOWN;
-            else if (c.poisoned) {  // game.py:473 would assert; payoffs were zeroed at :468
-#pragma unroll
-                for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + tile0 + s] = 0.0;
-                c.done = c.cont ? (int)((game_over<P>(v, s) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER)
-                                : (int)F_HAND_OVER;
-                c.pc = PC_DONE;
-            } else {
-                end_hand_finish<P>(v, s, m, c, pay, d.payoffs, d.stride, tile0 + s, a.gc);
-#pragma unroll
-                for (int p = 0; p < P; ++p) paysum[p] += pay[p];
+        // ---- park the envs whose hand ended; process the buffer when it is full
+        const bool parked = live && c.pc == PC_END_HAND;
+        const unsigned vote = __ballot_sync(0xffffffffu, parked);
+        const int k = __popc(vote);
+        if (k) {
+            if (e_count + k > 32) {
+                s_count = flush_end_hands<P>(warp_base, e_count, s_count, a);
+                e_count = 0;
             }
-            ctl[s] = pack_ctl(c);
-            v.meta[s] = pack_meta(m);
+            __syncwarp();
+            if (parked) move_slot<P>(w, lane, 32 + e_count + __popc(vote & ((1u << lane) - 1u)));
+            e_count += k;
+            if (e_count == 32) {
+                s_count = flush_end_hands<P>(warp_base, e_count, s_count, a);
+                e_count = 0;
+            }
         }
-        __syncthreads();
-        compact_slots(ctl, PC_SHOWDOWN, list_s, &s_count[1]);
-        __syncthreads();
-        const int n_s = s_count[1];
-        if (tid < n_s) {
-            const int s = list_s[tid];
-            Ctl c = unpack_ctl(ctl[s]);
-            Meta m = unpack_meta(v.meta[s]);
-            double pay[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) pay[p] = 0.0;
-            ++n_showdowns;
-            showdown<P>(v, s, c, pay, a.gc.seed, a.gc.env_id_base + (uint32_t)(tile0 + s), d.episode[tile0 + s]);
-            end_hand_finish<P>(v, s, m, c, pay, d.payoffs, d.stride, tile0 + s, a.gc);
-#pragma unroll
-            for (int p = 0; p < P; ++p) paysum[p] += pay[p];
-            ctl[s] = pack_ctl(c);
-            v.meta[s] = pack_meta(m);
-        }
-        __syncthreads();
+        __syncwarp();
     }
+    // ---- drain what is left in the buffers
+    if (e_count) s_count = flush_end_hands<P>(warp_base, e_count, s_count, a);
+    if (s_count) flush_showdowns<P>(warp_base, s_count, a);
 
-    // ---- epilogue, one thread per env: flags, auto-reset, valid mask of the new active player
-    uint32_t f = 0;
-    if (live) {
-        const Ctl c = unpack_ctl(ctl[tid]);
-        Meta m = unpack_meta(v.meta[tid]);
-        f = (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
-        if ((f & F_GAME_OVER) && !(f & (F_INVALID | F_POISONED)) && a.gc.auto_reset) {
-            d.episode[env] += 1;
-            reset_env<P>(v, tid, m, a.gc);
-            v.meta[tid] = pack_meta(m);
-        }
-        if (a.flags) a.flags[env] = (uint8_t)f;
-        if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(v, tid, m.act);
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            d.cr[p * d.stride + env] = v.cr[p * TILE + tid];
-            d.bt[p * d.stride + env] = v.bt[p * TILE + tid];
-            d.pd[p * d.stride + env] = v.pd[p * TILE + tid];
-            d.st[p * d.stride + env] = v.st[p * TILE + tid];
-        }
-        d.mr[env] = v.mr[tid];
-        d.meta[env] = v.meta[tid];
-        d.hand[env] = v.hand[tid];
-    }
-
-    // ---- K6: aggregate statistics (warp reduce -> shared -> one global atomic per block)
+    // ---- K6: statistics, one set of global atomics per warp for the whole launch
+    __syncwarp();
     if (a.gc.track_stats) {
-        const uint32_t cnt[STAT_COUNT] = {live && !(f & F_INVALID) ? 1u : 0u, n_hands, n_showdowns,
-                                          (f & F_GAME_OVER) ? 1u : 0u, (f & F_INVALID) ? 1u : 0u,
-                                          (f & F_POISONED) ? 1u : 0u};
-#pragma unroll
-        for (int i = 0; i < STAT_COUNT; ++i) {
-            const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[i]);
-            if ((tid & 31) == 0 && w) atomicAdd(&s_stats[i], (unsigned long long)w);
-        }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            double x = paysum[p];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if ((tid & 31) == 0 && x != 0.0) atomicAdd(&s_paysum[p], x);
-        }
-        __syncthreads();
-        if (tid < STAT_COUNT && s_stats[tid]) atomicAdd(&d.stats[tid], s_stats[tid]);
-        if (tid < P && s_paysum[tid] != 0.0) atomicAdd(&d.payoff_sum[tid], s_paysum[tid]);
+        if (lane < STAT_COUNT && w.wstat[lane]) atomicAdd(&d.stats[lane], (unsigned long long)w.wstat[lane]);
+        if (lane < P && w.wpay[lane] != 0.0) atomicAdd(&d.payoff_sum[lane], w.wpay[lane]);
     }
 }
 
@@ -488,14 +658,25 @@ static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsign
 template <int P, bool SAMPLE>
 static cudaError_t launch_step(const StepArgs& a, cudaStream_t s)
 {
-    constexpr size_t smem = tile_smem_bytes<P>();
-    static bool configured = false;  // per instantiation; the attribute is per function and device-wide
-    if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<P, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr size_t smem = warp_smem_bytes<P>() * STEP_WARPS;
+    static int grid_blocks[64] = {0};  // per device: persistent grid = SMs x resident blocks per SM
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!grid_blocks[dev]) {
+        e = cudaFuncSetAttribute(step_kernel<P, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<P, SAMPLE>, STEP_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        grid_blocks[dev] = (per_sm > 0 ? per_sm : 1) * sms;
     }
-    step_kernel<P, SAMPLE><<<(unsigned)(a.d.stride / TILE), TILE, smem, s>>>(a);
+    const size_t n_sub = a.d.stride / 32, want = (n_sub + STEP_WARPS - 1) / STEP_WARPS;
+    const unsigned grid = (unsigned)(want < (size_t)grid_blocks[dev] ? want : (size_t)grid_blocks[dev]);
+    step_kernel<P, SAMPLE><<<grid, STEP_WARPS * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 
