@@ -29,6 +29,10 @@ struct DevState {
     uint32_t *meta, *hand, *episode;
     unsigned long long* stats;  // [6] counters
     double* payoff_sum;         // [MAX_PLAYERS]
+    uint32_t* ctl;              // [stride] automaton control word of envs parked between the step kernels
+    uint32_t* list_e;           // [stride] envs whose hand ended in this step (work list of kernel B)
+    uint32_t* list_s;           // [stride] envs that need a ranked showdown (work list of kernel C)
+    uint32_t* counters;         // [4] list lengths: {e, s} x step parity
     uint64_t n, stride;
 };
 
@@ -44,27 +48,17 @@ struct StepArgs {
     uint32_t step_idx;
     uint32_t use_weights;
     uint32_t weights[NUM_MOVES];
+    uint32_t parity;  // which pair of list counters this step uses; the other pair is zeroed for the next step
 };
 
-constexpr int TILE = 256;   // env-count granularity of the HBM planes (stride is a multiple of it)
-constexpr int SLOTS = 96;   // per-warp shared-memory slots: 32 staging + 32 end-hand + 32 showdown
-constexpr int STEP_WARPS = 4;  // warps per block of the step kernel (each warp is autonomous)
+constexpr int TILE = 256;         // env-count granularity of the HBM planes (stride is a multiple of it)
+constexpr int STEP_THREADS = 128; // block size of the three step kernels (one env per thread)
 
+// bytes of shared memory per thread-slot: f64 planes (3P+1), meta/hand u32, P state bytes
 template <int P>
-__host__ __device__ constexpr size_t warp_smem_bytes();
-
-// resident blocks per SM the step kernel is compiled for: what 227 KB of shared memory allow, at most 7
-template <int P>
-__host__ __device__ constexpr int step_min_blocks()
+__host__ __device__ constexpr size_t slot_bytes()
 {
-    constexpr size_t per_block = warp_smem_bytes<P>() * STEP_WARPS + 1024;
-    constexpr int by_smem = (int)((size_t)232448 / per_block);
-#ifdef PKB_STEP_MAX_BLOCKS  // tuning knob for experiments
-    constexpr int cap = PKB_STEP_MAX_BLOCKS;
-#else
-    constexpr int cap = 7;
-#endif
-    return by_smem > cap ? cap : (by_smem < 1 ? 1 : by_smem);
+    return (size_t)(3 * P + 1) * 8 + 2 * 4 + P;
 }
 
 PKB_D View<0> global_view(const DevState& d)
@@ -72,342 +66,294 @@ PKB_D View<0> global_view(const DevState& d)
     return View<0>{d.cr, d.bt, d.pd, d.mr, d.st, d.meta, d.hand, (size_t)d.stride};
 }
 
-// The warp's shared-memory slots plus the control words kept beside the game state, and the
-// warp's statistics accumulators (written by lane 0 only)
+// Per-thread staging of one env in shared memory ([field][thread] layout: bank-conflict free, and
+// seats can be indexed dynamically without spilling register arrays to local memory)
 template <int P>
-struct WarpSlots {
-    View<SLOTS> v;
-    uint32_t* ctl;       // automaton control word (pkb_game.cuh, struct Ctl)
-    uint32_t* env;       // local env index of the slot's occupant
-    uint32_t* wstat;     // [STAT_COUNT] per-warp counters
-    double* wpay;        // [P] per-warp payoff sums
-};
-
-template <int P>
-__host__ __device__ constexpr size_t warp_smem_bytes()
+PKB_D View<STEP_THREADS> carve_view(unsigned char* smem)
 {
-    // per slot: f64 planes (3P+1), meta/hand/ctl/env u32, P state bytes; then P f64 + 8 u32 of statistics
-    return (size_t)SLOTS * ((3 * P + 1) * 8 + 4 * 4 + P) + (size_t)P * 8 + 32;
+    View<STEP_THREADS> v;
+    double* f64 = reinterpret_cast<double*>(smem);
+    v.cr = f64;
+    v.bt = f64 + P * STEP_THREADS;
+    v.pd = f64 + 2 * P * STEP_THREADS;
+    v.mr = f64 + 3 * P * STEP_THREADS;
+    uint32_t* u32 = reinterpret_cast<uint32_t*>(f64 + (3 * P + 1) * STEP_THREADS);
+    v.meta = u32;
+    v.hand = u32 + STEP_THREADS;
+    v.st = reinterpret_cast<uint8_t*>(u32 + 2 * STEP_THREADS);
+    v.ld_rt = STEP_THREADS;
+    return v;
 }
 
 template <int P>
-PKB_D WarpSlots<P> carve_slots(unsigned char* base)
+PKB_D void load_env(View<STEP_THREADS>& v, int t, const DevState& d, size_t env)
 {
-    WarpSlots<P> w;
-    double* f64 = reinterpret_cast<double*>(base);
-    w.v.cr = f64;
-    w.v.bt = f64 + P * SLOTS;
-    w.v.pd = f64 + 2 * P * SLOTS;
-    w.v.mr = f64 + 3 * P * SLOTS;
-    w.wpay = f64 + (3 * P + 1) * SLOTS;
-    uint32_t* u32 = reinterpret_cast<uint32_t*>(f64 + (3 * P + 1) * SLOTS + P);
-    w.v.meta = u32;
-    w.v.hand = u32 + SLOTS;
-    w.ctl = u32 + 2 * SLOTS;
-    w.env = u32 + 3 * SLOTS;
-    w.wstat = u32 + 4 * SLOTS;
-    w.v.st = reinterpret_cast<uint8_t*>(u32 + 4 * SLOTS + 8);
-    w.v.ld_rt = SLOTS;
-    return w;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        v.cr[p * STEP_THREADS + t] = d.cr[p * d.stride + env];
+        v.bt[p * STEP_THREADS + t] = d.bt[p * d.stride + env];
+        v.pd[p * STEP_THREADS + t] = d.pd[p * d.stride + env];
+        v.st[p * STEP_THREADS + t] = d.st[p * d.stride + env];
+    }
+    v.mr[t] = d.mr[env];
+    v.meta[t] = d.meta[env];
+    v.hand[t] = d.hand[env];
 }
 
-// warp-level event counter: lane 0 adds the number of lanes for which `event` holds
-PKB_D void count_event(uint32_t* counter, bool event)
+template <int P>
+PKB_D void store_env(const View<STEP_THREADS>& v, int t, const DevState& d, size_t env)
+{
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        d.cr[p * d.stride + env] = v.cr[p * STEP_THREADS + t];
+        d.bt[p * d.stride + env] = v.bt[p * STEP_THREADS + t];
+        d.pd[p * d.stride + env] = v.pd[p * STEP_THREADS + t];
+        d.st[p * d.stride + env] = v.st[p * STEP_THREADS + t];
+    }
+    d.mr[env] = v.mr[t];
+    d.meta[env] = v.meta[t];
+    d.hand[env] = v.hand[t];
+}
+
+// warp-aggregated append of env ids to a work list
+PKB_D void list_append(uint32_t* list, uint32_t* counter, bool mine, uint32_t env)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned vote = __ballot_sync(0xffffffffu, mine);
+    if (!vote) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine) list[base + __popc(vote & ((1u << lane) - 1u))] = env;
+}
+
+// warp-aggregated event counter -> one global atomic per warp that saw the event
+PKB_D void count_events(unsigned long long* counter, bool event)
 {
     const unsigned vote = __ballot_sync(0xffffffffu, event);
-    if (vote && (threadIdx.x & 31) == 0) *counter += (uint32_t)__popc(vote);
+    if (vote && (threadIdx.x & 31) == 0) atomicAdd(counter, (unsigned long long)__popc(vote));
 }
 
+// Step outputs of one finished env: flag bits and the valid mask of the new active player
 template <int P>
-PKB_D void move_slot(WarpSlots<P>& w, int from, int to)
+PKB_D uint32_t write_outputs(const View<STEP_THREADS>& v, int t, const Ctl& c, const StepArgs& a, size_t env)
 {
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        w.v.cr[p * SLOTS + to] = w.v.cr[p * SLOTS + from];
-        w.v.bt[p * SLOTS + to] = w.v.bt[p * SLOTS + from];
-        w.v.pd[p * SLOTS + to] = w.v.pd[p * SLOTS + from];
-        w.v.st[p * SLOTS + to] = w.v.st[p * SLOTS + from];
-    }
-    w.v.mr[to] = w.v.mr[from];
-    w.v.meta[to] = w.v.meta[from];
-    w.v.hand[to] = w.v.hand[from];
-    w.ctl[to] = w.ctl[from];
-    w.env[to] = w.env[from];
-}
-
-// ---- out-of-line pieces: ONE copy each in the kernel image.  The step kernel's warps run
-//      different phases at the same time, so its code must stay small enough for the SM's
-//      instruction cache; everything below takes and returns plain words.
-__device__ __noinline__ uint32_t rank7_call(uint64_t mask) { return eval_mask52(mask); }
-
-template <int P>
-__device__ __noinline__ uint32_t setup_hand_call(unsigned char* warp_base, int slot, uint32_t meta_word, const GameConst& gc)
-{
-    WarpSlots<P> w = carve_slots<P>(warp_base);
-    Meta m = unpack_meta(meta_word);
-    setup_hand<P>(w.v, slot, m, gc);
-    return pack_meta(m);
-}
-
-template <int P>
-__device__ __noinline__ void showdown_call(unsigned char* warp_base, int slot, uint32_t ctl_word, uint64_t seed,
-                                           uint32_t env_id, uint32_t episode)
-{
-    WarpSlots<P> w = carve_slots<P>(warp_base);
-    showdown<P>(w.v, slot, unpack_ctl(ctl_word), seed, env_id, episode, [](uint64_t m) { return rank7_call(m); });
-}
-
-// Step epilogue for one finished env: flags, valid mask of the new active player, state back to HBM.
-// Warp-uniform call; `active` selects the lanes that retire their slot.
-template <int P>
-PKB_D void retire_slot(WarpSlots<P>& w, int slot, bool active, const StepArgs& a)
-{
-    const DevState& d = a.d;
-    Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
-    if (active) c = unpack_ctl(w.ctl[slot]);
     const uint32_t f = (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
-    if (a.gc.track_stats) {
-        count_event(&w.wstat[STAT_STEPS], active && !c.invalid);
-        count_event(&w.wstat[STAT_GAMES], active && (f & F_GAME_OVER));
-        count_event(&w.wstat[STAT_INVALID], active && c.invalid);
-        count_event(&w.wstat[STAT_POISONED], active && c.poisoned);
-    }
-    if (!active) return;
-    const size_t env = w.env[slot];
     if (a.flags) a.flags[env] = (uint8_t)f;
-    if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(w.v, slot, unpack_meta(w.v.meta[slot]).act);
-    if (c.invalid) return;  // nothing changed (game.py:649-651 raises before any mutation)
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        d.cr[p * d.stride + env] = w.v.cr[p * SLOTS + slot];
-        d.bt[p * d.stride + env] = w.v.bt[p * SLOTS + slot];
-        d.pd[p * d.stride + env] = w.v.pd[p * SLOTS + slot];
-        d.st[p * d.stride + env] = w.v.st[p * SLOTS + slot];
-    }
-    d.mr[env] = w.v.mr[slot];
-    d.meta[env] = w.v.meta[slot];
-    d.hand[env] = w.v.hand[slot];
+    if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(v, t, unpack_meta(v.meta[t]).act);
+    return f;
 }
 
-// What follows Game.end_hand once the payoffs are in the pending plane: finish the hand, deal the next
-// one, resume the seat scan -- and any further hand that ends inside the same step (rare: all-in blinds
-// make whole hands play themselves) -- then auto-reset if asked.  Warp-uniform, out of line.
-// `ctl_word` must have pc == PC_END_HAND semantics already resolved by end_hand_begin (+ showdown);
-// `asserted`: end_hand_begin found no potential winner (game.py:473 would raise AssertionError).
+// What follows Game.end_hand once the payoffs are in the pending plane (game.py:530-539 and the
+// caller's use of the return value), then Game.reset() if the game ended and auto-reset is on.
+// Leaves c.pc == PC_END_HAND when ANOTHER hand ends inside the same step (rare: all-in blinds).
 template <int P>
-__device__ __noinline__ uint32_t finish_hand_call(unsigned char* warp_base, int slot, uint32_t ctl_word, bool active,
-                                                  bool asserted, const StepArgs& a)
+PKB_D void finish_hand(View<STEP_THREADS>& v, int t, Meta& m, Ctl& c, const StepArgs& a, size_t env, double (&paysum)[P])
 {
-    WarpSlots<P> w = carve_slots<P>(warp_base);
     const DevState& d = a.d;
-    Ctl c = unpack_ctl(ctl_word);
+    double pay[P];
+    end_hand_finish<P>(v, t, m, c, d.payoffs, d.stride, env, pay, [&](Meta mm) {
+        setup_hand<P>(v, t, mm, a.gc);
+        return mm;
+    });
+#pragma unroll
+    for (int p = 0; p < P; ++p) paysum[p] += pay[p];
+    if (c.pc == PC_DONE && (c.done & (int)F_GAME_OVER) && !c.poisoned && a.gc.auto_reset) {
+        d.episode[env] += 1;  // Game.reset() right after the step that ended the game (game.py:397-412)
+        reset_env<P>(v, t, m, a.gc);
+    }
+}
+
+// game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
+// reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED.
+template <int P>
+PKB_D void assert_exit(const View<STEP_THREADS>& v, int t, Ctl& c, const StepArgs& a, size_t env)
+{
+#pragma unroll
+    for (int p = 0; p < P; ++p) a.d.payoffs[p * a.d.stride + env] = 0.0;
+    c.done = c.cont ? (int)((game_over<P>(v, t) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
+    c.pc = PC_DONE;
+}
+
+// block reduction of the per-thread payoff sums and counters into the handle's statistics
+template <int P>
+PKB_D void reduce_stats(const DevState& d, const double (&paysum)[P], uint32_t hands, uint32_t shows, uint32_t games,
+                        uint32_t poisoned)
+{
+    __shared__ double s_pay[MAX_PLAYERS];
+    __shared__ uint32_t s_cnt[4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < MAX_PLAYERS) s_pay[tid] = 0.0;
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t cnt[4] = {hands, shows, games, poisoned};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[i]);
+        if (lane == 0 && w) atomicAdd(&s_cnt[i], w);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        double x = paysum[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x != 0.0) atomicAdd(&s_pay[p], x);
+    }
+    __syncthreads();
+    if (tid == 0 && s_cnt[0]) atomicAdd(&d.stats[STAT_HANDS], (unsigned long long)s_cnt[0]);
+    if (tid == 1 && s_cnt[1]) atomicAdd(&d.stats[STAT_SHOWDOWNS], (unsigned long long)s_cnt[1]);
+    if (tid == 2 && s_cnt[2]) atomicAdd(&d.stats[STAT_GAMES], (unsigned long long)s_cnt[2]);
+    if (tid == 3 && s_cnt[3]) atomicAdd(&d.stats[STAT_POISONED], (unsigned long long)s_cnt[3]);
+    if (tid >= 32 && tid < 32 + P && s_pay[tid - 32] != 0.0) atomicAdd(&d.payoff_sum[tid - 32], s_pay[tid - 32]);
+}
+
+// --------------------------------------------------------------------------------------------
+// Game.step (game.py:621-700) as a three-kernel pipeline over the SoA planes.  The branches of a
+// step differ by 10-100x in cost (a bet; a hand that ends; a ranked showdown), so instead of letting
+// warps diverge, each kernel runs ONE kind of work at full warp width and hands the rest on
+// through a compacted env list in HBM:
+//   A  every env:          validate/sample the action, bet, seat scan, next_turn commits  -> list E
+//   B  envs in list E:     end_hand: commit, last-stand pots, deal the next hand, resume    -> list S
+//   C  envs in list S:     ranked showdown (deal replay, 7-card ranks, side pots), then as B
+// Each kernel is small (instruction-cache resident) and streams state through shared memory.
+// --------------------------------------------------------------------------------------------
+
+// K1: one thread per env, fully coalesced loads/stores
+template <int P, bool SAMPLE>
+__global__ void __launch_bounds__(STEP_THREADS) step_kernel_a(const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    View<STEP_THREADS> v = carve_view<P>(smem_raw);
+    const DevState& d = a.d;
+    const int t = threadIdx.x;
+    const size_t env = (size_t)blockIdx.x * STEP_THREADS + t;
+    const bool live = env < d.n;
+    if (blockIdx.x == 0 && t < 2) d.counters[2 * (a.parity ^ 1u) + t] = 0;  // next step's list lengths
+
+    load_env<P>(v, t, d, env);  // stride is a multiple of the block size: always in bounds
+    Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+        Meta m = unpack_meta(v.meta[t]);
+        const uint32_t vm = valid_mask<P>(v, t, m.act);
+        int action;
+        if (SAMPLE) {
+            action = sample_action(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx, vm,
+                                   a.use_weights ? a.weights : nullptr);
+            if (a.actions_out) a.actions_out[env] = action;
+        } else
+            action = a.actions[env];
+        step_begin<P>(v, t, m, c, action, vm, a.gc);
+        v.meta[t] = pack_meta(m);
+    }
+    const bool parked = live && c.pc == PC_END_HAND;
+    if (live) {
+        if (!c.invalid) store_env<P>(v, t, d, env);  // an invalid action changes nothing (game.py:649-651)
+        if (parked) d.ctl[env] = pack_ctl(c);
+        else write_outputs<P>(v, t, c, a, env);
+    }
+    list_append(d.list_e, &d.counters[2 * a.parity], parked, (uint32_t)env);
+    if (a.gc.track_stats) {
+        count_events(&d.stats[STAT_INVALID], live && c.invalid);
+        count_events(&d.stats[STAT_POISONED], live && c.poisoned);
+        if (blockIdx.x == 0 && t == 0) atomicAdd(&d.stats[STAT_STEPS], (unsigned long long)d.n);  // minus invalid: see pkb_stats
+    }
+}
+
+// K2a: end_hand for the envs in list E
+template <int P>
+__global__ void __launch_bounds__(STEP_THREADS) step_kernel_b(const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    View<STEP_THREADS> v = carve_view<P>(smem_raw);
+    const DevState& d = a.d;
+    const int t = threadIdx.x;
+    const uint32_t n_items = d.counters[2 * a.parity];
+    uint32_t games = 0, poisoned = 0;
     double paysum[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) paysum[p] = 0.0;
-    uint32_t more_hands = 0, more_shows = 0;
-    if (active) {
-        Meta m = unpack_meta(w.v.meta[slot]);
-        const size_t env = w.env[slot];
-        const auto deal = [&](const Meta& mm) { return unpack_meta(setup_hand_call<P>(warp_base, slot, pack_meta(mm), a.gc)); };
-        while (!asserted) {
-            double pay[P];
-            end_hand_finish<P>(w.v, slot, m, c, d.payoffs, d.stride, env, pay, deal);
-#pragma unroll
-            for (int p = 0; p < P; ++p) paysum[p] += pay[p];
-            if (c.pc != PC_END_HAND) break;
-            ++more_hands;  // another hand ended inside this step
-            if (end_hand_begin<P>(w.v, slot, c)) {
-                ++more_shows;
-                showdown_call<P>(warp_base, slot, pack_ctl(c), a.gc.seed, a.gc.env_id_base + (uint32_t)env, d.episode[env]);
-            } else if (c.poisoned)
-                asserted = true;
-        }
-        if (asserted) {  // payoffs were zeroed at game.py:468 before the assert
-#pragma unroll
-            for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
-            c.done = c.cont ? (int)((game_over<P>(w.v, slot) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER)
-                            : (int)F_HAND_OVER;
-            c.pc = PC_DONE;
-        } else if ((c.done & (int)F_GAME_OVER) && !c.poisoned && a.gc.auto_reset) {
-            // Game.reset() right after the step that ended the game (game.py:397-412)
-            d.episode[env] += 1;
-            m.dealer = a.gc.dealer;
-            m.act = 0;
-            w.v.hand[slot] = 0;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                w.v.cr[p * SLOTS + slot] = a.gc.start_credits[p];
-                w.v.st[p * SLOTS + slot] = ST_ACTIVE;
+    const uint32_t rounded = (n_items + STEP_THREADS - 1) / STEP_THREADS * STEP_THREADS;
+    for (uint32_t i = blockIdx.x * STEP_THREADS + t; i < rounded; i += gridDim.x * STEP_THREADS) {
+        const bool active = i < n_items;
+        bool to_c = false;
+        size_t env = 0;
+        if (active) {
+            env = d.list_e[i];
+            load_env<P>(v, t, d, env);
+            Ctl c = unpack_ctl(d.ctl[env]);
+            Meta m = unpack_meta(v.meta[t]);
+            if (end_hand_begin<P>(v, t, c)) {
+                c.pc = PC_SHOWDOWN;
+                to_c = true;
+            } else if (c.poisoned) {
+                assert_exit<P>(v, t, c, a, env);
+            } else {
+                finish_hand<P>(v, t, m, c, a, env, paysum);
+                to_c = c.pc == PC_END_HAND;  // another hand ends inside this step: kernel C runs it
             }
-            m = deal(m);
+            v.meta[t] = pack_meta(m);
+            store_env<P>(v, t, d, env);
+            if (to_c) d.ctl[env] = pack_ctl(c);
+            else {
+                const uint32_t f = write_outputs<P>(v, t, c, a, env);
+                games += (f & F_GAME_OVER) ? 1u : 0u;
+                poisoned += c.poisoned ? 1u : 0u;
+            }
         }
-        w.v.meta[slot] = pack_meta(m);
+        list_append(d.list_s, &d.counters[2 * a.parity + 1], to_c, (uint32_t)env);
     }
     if (a.gc.track_stats) {
-        const uint32_t h = __reduce_add_sync(0xffffffffu, more_hands), sh = __reduce_add_sync(0xffffffffu, more_shows);
-        if ((threadIdx.x & 31) == 0) {
-            w.wstat[STAT_HANDS] += h;
-            w.wstat[STAT_SHOWDOWNS] += sh;
-        }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            double x = paysum[p];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) == 0) w.wpay[p] += x;
-        }
+        const uint32_t hands = (blockIdx.x == 0 && t == 0) ? n_items : 0u;
+        reduce_stats<P>(d, paysum, hands, 0u, games, poisoned);
     }
-    return pack_ctl(c);
 }
 
-// Ranked showdowns of the warp's showdown buffer (slots 64..64+count), one env per lane
+// K2b: ranked showdowns (and the rare further hands of a step) for the envs in list S
 template <int P>
-__device__ __noinline__ void flush_showdowns(unsigned char* warp_base, int s_count, const StepArgs& a)
-{
-    WarpSlots<P> w = carve_slots<P>(warp_base);
-    const int lane = threadIdx.x & 31, slot = 64 + lane;
-    const bool active = lane < s_count;
-    __syncwarp();
-    uint32_t ctl_word = 0;
-    if (active) {
-        ctl_word = w.ctl[slot];
-        const size_t env = w.env[slot];
-        showdown_call<P>(warp_base, slot, ctl_word, a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.d.episode[env]);
-    }
-    if (a.gc.track_stats) count_event(&w.wstat[STAT_SHOWDOWNS], active);
-    ctl_word = finish_hand_call<P>(warp_base, slot, ctl_word, active, false, a);
-    if (active) w.ctl[slot] = ctl_word;
-    retire_slot<P>(w, slot, active, a);
-    __syncwarp();
-}
-
-// end_hand for the warp's end-hand buffer (slots 32..32+count): last-stand hands finish here,
-// ranked hands move on to the showdown buffer.  Returns the new fill of the showdown buffer.
-template <int P>
-__device__ __noinline__ int flush_end_hands(unsigned char* warp_base, int e_count, int s_count, const StepArgs& a)
-{
-    WarpSlots<P> w = carve_slots<P>(warp_base);
-    const int lane = threadIdx.x & 31, slot = 32 + lane;
-    const bool active = lane < e_count;
-    __syncwarp();
-    bool ranked = false;
-    uint32_t ctl_word = 0;
-    bool asserted = false;
-    if (active) {
-        Ctl c = unpack_ctl(w.ctl[slot]);
-        ranked = end_hand_begin<P>(w.v, slot, c);
-        asserted = !ranked && c.poisoned;
-        if (ranked) c.pc = PC_SHOWDOWN;
-        ctl_word = pack_ctl(c);
-        w.ctl[slot] = ctl_word;
-    }
-    if (a.gc.track_stats) count_event(&w.wstat[STAT_HANDS], active);
-    ctl_word = finish_hand_call<P>(warp_base, slot, ctl_word, active && !ranked, asserted, a);
-    if (active && !ranked) w.ctl[slot] = ctl_word;
-    retire_slot<P>(w, slot, active && !ranked, a);
-    const unsigned vote = __ballot_sync(0xffffffffu, ranked);
-    const int k = __popc(vote);
-    if (k) {
-        if (s_count + k > 32) {
-            flush_showdowns<P>(warp_base, s_count, a);
-            s_count = 0;
-        }
-        __syncwarp();
-        if (ranked) move_slot<P>(w, slot, 64 + s_count + __popc(vote & ((1u << lane) - 1u)));
-        s_count += k;
-        if (s_count == 32) {
-            flush_showdowns<P>(warp_base, s_count, a);
-            s_count = 0;
-        }
-    }
-    __syncwarp();
-    return s_count;
-}
-
-// --------------------------------------------------------------------------------------------
-// K1/K2: Game.step (game.py:621-700).  Persistent grid; every warp owns 96 shared-memory slots
-// and walks 32-env sub-tiles on its own: phase A (validate, bet, scan seats) runs one env per lane
-// on the staging slots; envs whose hand ends are parked in the warp's end-hand buffer and those
-// that need ranking in its showdown buffer, and each buffer is processed when it fills, so the
-// expensive branches run at (nearly) full warp width without any block-level barrier.
-// --------------------------------------------------------------------------------------------
-template <int P, bool SAMPLE>
-__global__ void __launch_bounds__(STEP_WARPS * 32, step_min_blocks<P>()) step_kernel(const __grid_constant__ StepArgs a)
+__global__ void __launch_bounds__(STEP_THREADS) step_kernel_c(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char* warp_base = smem_raw + (size_t)wib * warp_smem_bytes<P>();
-    WarpSlots<P> w = carve_slots<P>(warp_base);
+    View<STEP_THREADS> v = carve_view<P>(smem_raw);
     const DevState& d = a.d;
-    if (lane < 8) w.wstat[lane] = 0;
-    if (lane < P) w.wpay[lane] = 0.0;
-    int e_count = 0, s_count = 0;  // warp-uniform fill of the end-hand / showdown buffers
-    __syncwarp();
-
-    const size_t n_sub = d.stride / 32, total_warps = (size_t)gridDim.x * STEP_WARPS;
-    for (size_t sub = (size_t)blockIdx.x * STEP_WARPS + wib; sub < n_sub; sub += total_warps) {
-        const size_t env = sub * 32 + lane;
-        const bool live = env < d.n;
-        // ---- stage 32 envs: HBM planes -> staging slots (slot = lane; 256 B per plane row)
+    const int t = threadIdx.x;
+    const uint32_t n_items = d.counters[2 * a.parity + 1];
+    uint32_t hands = 0, shows = 0, games = 0, poisoned = 0;
+    double paysum[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            w.v.cr[p * SLOTS + lane] = d.cr[p * d.stride + env];
-            w.v.bt[p * SLOTS + lane] = d.bt[p * d.stride + env];
-            w.v.pd[p * SLOTS + lane] = d.pd[p * d.stride + env];
-            w.v.st[p * SLOTS + lane] = d.st[p * d.stride + env];
-        }
-        w.v.mr[lane] = d.mr[env];
-        w.v.meta[lane] = d.meta[env];
-        w.v.hand[lane] = d.hand[env];
-        w.env[lane] = (uint32_t)env;
-
-        // ---- phase A: validate the action, bet, scan seats up to the first end_hand
-        Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
-        if (live) {
-            Meta m = unpack_meta(w.v.meta[lane]);
-            const uint32_t vm = valid_mask<P>(w.v, lane, m.act);
-            int action;
-            if (SAMPLE) {
-                action = sample_action(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx, vm,
-                                       a.use_weights ? a.weights : nullptr);
-                if (a.actions_out) a.actions_out[env] = action;
-            } else
-                action = a.actions[env];
-            step_begin<P>(w.v, lane, m, c, action, vm, a.gc);
-            w.v.meta[lane] = pack_meta(m);
-        }
-        w.ctl[lane] = pack_ctl(c);
-        retire_slot<P>(w, lane, live && c.pc == PC_DONE, a);
-
-        // ---- park the envs whose hand ended; process the buffer when it is full
-        const bool parked = live && c.pc == PC_END_HAND;
-        const unsigned vote = __ballot_sync(0xffffffffu, parked);
-        const int k = __popc(vote);
-        if (k) {
-            if (e_count + k > 32) {
-                s_count = flush_end_hands<P>(warp_base, e_count, s_count, a);
-                e_count = 0;
+    for (int p = 0; p < P; ++p) paysum[p] = 0.0;
+    for (uint32_t i = blockIdx.x * STEP_THREADS + t; i < n_items; i += gridDim.x * STEP_THREADS) {
+        const size_t env = d.list_s[i];
+        load_env<P>(v, t, d, env);
+        Ctl c = unpack_ctl(d.ctl[env]);
+        Meta m = unpack_meta(v.meta[t]);
+        const uint32_t episode = d.episode[env];
+        bool asserted = false;
+        while (c.pc != PC_DONE) {
+            bool ranked = c.pc == PC_SHOWDOWN;
+            if (!ranked) {  // PC_END_HAND: a further hand of this step, from its beginning
+                ++hands;
+                ranked = end_hand_begin<P>(v, t, c);
+                if (!ranked && c.poisoned) {
+                    asserted = true;
+                    break;
+                }
             }
-            __syncwarp();
-            if (parked) move_slot<P>(w, lane, 32 + e_count + __popc(vote & ((1u << lane) - 1u)));
-            e_count += k;
-            if (e_count == 32) {
-                s_count = flush_end_hands<P>(warp_base, e_count, s_count, a);
-                e_count = 0;
+            if (ranked) {
+                ++shows;
+                showdown<P>(v, t, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode,
+                            [](uint64_t mask) { return eval_mask52(mask); });
             }
+            c.pc = PC_DONE;
+            finish_hand<P>(v, t, m, c, a, env, paysum);
         }
-        __syncwarp();
+        if (asserted) assert_exit<P>(v, t, c, a, env);
+        v.meta[t] = pack_meta(m);
+        store_env<P>(v, t, d, env);
+        const uint32_t f = write_outputs<P>(v, t, c, a, env);
+        games += (f & F_GAME_OVER) ? 1u : 0u;
+        poisoned += c.poisoned ? 1u : 0u;
     }
-    // ---- drain what is left in the buffers
-    if (e_count) s_count = flush_end_hands<P>(warp_base, e_count, s_count, a);
-    if (s_count) flush_showdowns<P>(warp_base, s_count, a);
-
-    // ---- K6: statistics, one set of global atomics per warp for the whole launch
-    __syncwarp();
-    if (a.gc.track_stats) {
-        if (lane < STAT_COUNT && w.wstat[lane]) atomicAdd(&d.stats[lane], (unsigned long long)w.wstat[lane]);
-        if (lane < P && w.wpay[lane] != 0.0) atomicAdd(&d.payoff_sum[lane], w.wpay[lane]);
-    }
+    if (a.gc.track_stats) reduce_stats<P>(d, paysum, hands, shows, games, poisoned);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -619,6 +565,7 @@ struct pkb_env {
     void* arena;
     size_t arena_bytes;
     uint32_t* d_weights;
+    uint32_t parity;  // step parity: which pair of list counters the next step uses
 };
 
 static thread_local std::string g_error;
@@ -658,25 +605,23 @@ static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsign
 template <int P, bool SAMPLE>
 static cudaError_t launch_step(const StepArgs& a, cudaStream_t s)
 {
-    constexpr size_t smem = warp_smem_bytes<P>() * STEP_WARPS;
-    static int grid_blocks[64] = {0};  // per device: persistent grid = SMs x resident blocks per SM
+    constexpr size_t smem = slot_bytes<P>() * STEP_THREADS;
+    static int sm_count[64] = {0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) dev = 0;
-    if (!grid_blocks[dev]) {
-        e = cudaFuncSetAttribute(step_kernel<P, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!sm_count[dev]) {
+        e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<P, SAMPLE>, STEP_WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        grid_blocks[dev] = (per_sm > 0 ? per_sm : 1) * sms;
     }
-    const size_t n_sub = a.d.stride / 32, want = (n_sub + STEP_WARPS - 1) / STEP_WARPS;
-    const unsigned grid = (unsigned)(want < (size_t)grid_blocks[dev] ? want : (size_t)grid_blocks[dev]);
-    step_kernel<P, SAMPLE><<<grid, STEP_WARPS * 32, smem, s>>>(a);
+    const unsigned blocks_a = (unsigned)(a.d.stride / STEP_THREADS);
+    // B and C read their item count on the device; a few waves of blocks walk the list with a grid stride
+    const unsigned cap = (unsigned)sm_count[dev] * 8u;
+    const unsigned blocks_bc = blocks_a < cap ? blocks_a : cap;
+    step_kernel_a<P, SAMPLE><<<blocks_a, STEP_THREADS, smem, s>>>(a);
+    step_kernel_b<P><<<blocks_bc, STEP_THREADS, smem, s>>>(a);
+    step_kernel_c<P><<<blocks_bc, STEP_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -711,9 +656,9 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     const int P = cfg->num_players;
     const uint64_t n = cfg->num_envs, stride = (n + TILE - 1) / TILE * TILE;
     // arena: f64 planes | u32 planes | u8 planes | stats
-    const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)3 * stride, n_u8 = (size_t)P * stride;
+    const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)6 * stride, n_u8 = (size_t)P * stride;
     const size_t off_u32 = n_f64 * 8, off_u8 = off_u32 + n_u32 * 4, off_stats = (off_u8 + n_u8 + 255) / 256 * 256;
-    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4;
+    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 4 * 4;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) {
         delete h;
@@ -737,10 +682,14 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     d.meta = u;
     d.hand = u + stride;
     d.episode = u + 2 * stride;
+    d.ctl = u + 3 * stride;
+    d.list_e = u + 4 * stride;
+    d.list_s = u + 5 * stride;
     d.st = reinterpret_cast<uint8_t*>(base + off_u8);
     d.stats = reinterpret_cast<unsigned long long*>(base + off_stats);
     d.payoff_sum = reinterpret_cast<double*>(base + off_stats + STAT_COUNT * 8);
     h->d_weights = reinterpret_cast<uint32_t*>(base + off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8);
+    d.counters = h->d_weights + NUM_MOVES + 1;
     d.n = n;
     d.stride = stride;
 
@@ -801,6 +750,8 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.valid = valid;
     a.step_idx = step_idx;
     a.use_weights = weights ? 1u : 0u;
+    a.parity = h->parity;
+    h->parity ^= 1u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaSuccess;
@@ -905,7 +856,7 @@ int pkb_stats(pkb_env* h, pkb_stats_t* out, void* stream)
     PKB_CUDA(cudaMemcpyAsync(c, h->d.stats, sizeof c, cudaMemcpyDeviceToHost, s));
     PKB_CUDA(cudaMemcpyAsync(ps, h->d.payoff_sum, sizeof ps, cudaMemcpyDeviceToHost, s));
     PKB_CUDA(cudaStreamSynchronize(s));
-    out->steps = c[STAT_STEPS];
+    out->steps = c[STAT_STEPS] - c[STAT_INVALID];  // kernel A adds num_envs per launch
     out->hands = c[STAT_HANDS];
     out->showdowns = c[STAT_SHOWDOWNS];
     out->games = c[STAT_GAMES];
