@@ -4,9 +4,14 @@
 // Everything here follows the reference line by line, including its non-standard behaviours
 // (SURVEY.md Appendix C): money is IEEE double, products are never fused into adds
 // (game.py:370-371, 675-678), sums follow numpy's add.reduce order, and the winner scan keeps
-// the judger.py:148 behaviour.  A View addresses element (seat p, slot s) of a plane at
-// plane[p * ld + s]; the same code runs on a shared-memory tile (ld = tile width) and directly
-// on the HBM planes (ld = padded env count).
+// the judger.py:148 behaviour.
+//
+// Representation: while an env is being processed its per-seat PlayerState bytes are held as four
+// disjoint bit masks in registers (struct Seats; FOLDED = in none of them), so every np.sum /
+// np.argmax / np.roll over player_states of the reference (game.py:320, 337, 421, 471, 567-572,
+// 598-599, 683) is a popcount / find-first-set instead of a loop over seats.  Money planes are
+// addressed through a View: element (seat p, slot s) of a plane is plane[p * ld + s]; the same
+// code runs on a shared-memory staging tile and directly on the HBM planes.
 #pragma once
 #include "pkb_common.cuh"
 #include "pkb_eval.cuh"
@@ -35,7 +40,7 @@ struct View {
     double* bt;      // bets             [P][ld]
     double* pd;      // pending_bets     [P][ld]
     double* mr;      // minimum_raise    [ld]
-    uint8_t* st;     // player_states    [P][ld]
+    uint8_t* st;     // player_states    [P][ld]  (read/written only by load_seats / store_seats)
     uint32_t* meta;  // packed indices   [ld]
     uint32_t* hand;  // hand counter     [ld]
     size_t ld_rt;
@@ -53,6 +58,55 @@ PKB_D Meta unpack_meta(uint32_t w)
 PKB_D uint32_t pack_meta(const Meta& m)
 {
     return (uint32_t)m.turn | (uint32_t)m.dealer << 3 | (uint32_t)m.sb << 8 | (uint32_t)m.bb << 13 | (uint32_t)m.act << 18;
+}
+
+// ---- seat-state masks (enums.py:130-134: FOLDED 0, ACTIVE 1, CALLED 2, ALL_IN 3, BROKEN 4) -------
+struct Seats {
+    uint32_t active, called, allin, broken;  // bit p = seat p; disjoint; FOLDED = none of them
+};
+
+template <int P>
+PKB_D constexpr uint32_t all_seats() { return (1u << P) - 1u; }
+
+template <int P, class V>
+PKB_D Seats load_seats(const V& v, size_t s)
+{
+    Seats x{0, 0, 0, 0};
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const uint32_t st = v.st[p * v.ld() + s];
+        x.active |= (uint32_t)(st == ST_ACTIVE) << p;
+        x.called |= (uint32_t)(st == ST_CALLED) << p;
+        x.allin |= (uint32_t)(st == ST_ALL_IN) << p;
+        x.broken |= (uint32_t)(st == ST_BROKEN) << p;
+    }
+    return x;
+}
+
+template <int P, class V>
+PKB_D void store_seats(V& v, size_t s, const Seats& x)
+{
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        v.st[p * v.ld() + s] = (uint8_t)((x.active >> p & 1u) * ST_ACTIVE + (x.called >> p & 1u) * ST_CALLED +
+                                         (x.allin >> p & 1u) * ST_ALL_IN + (x.broken >> p & 1u) * ST_BROKEN);
+}
+
+// player_states[p] = state
+PKB_D void set_state(Seats& x, int p, int state)
+{
+    const uint32_t bit = 1u << p, keep = ~bit;
+    x.active = (x.active & keep) | (state == ST_ACTIVE ? bit : 0u);
+    x.called = (x.called & keep) | (state == ST_CALLED ? bit : 0u);
+    x.allin = (x.allin & keep) | (state == ST_ALL_IN ? bit : 0u);
+    x.broken = (x.broken & keep) | (state == ST_BROKEN ? bit : 0u);
+}
+
+// first set bit of `mask` at or after seat `idx` in cyclic order; mask != 0, idx < 32
+PKB_D int first_from(uint32_t mask, int idx)
+{
+    const uint32_t hi = mask >> idx << idx;
+    return __ffs((int)(hi ? hi : mask)) - 1;
 }
 
 // numpy float64 add.reduce order (pairwise_sum): n < 8 left to right from 0.0; n >= 8 eight lanes,
@@ -83,18 +137,12 @@ PKB_D double sum_plane(const V& v, const double* plane, size_t s)
 }
 
 // Game.get_first_playing, game.py:334-337; idx in [0, 2P)
-template <int P, class V>
-PKB_D int first_playing(const V& v, size_t s, int idx)
+template <int P>
+PKB_D int first_playing(const Seats& x, int idx)
 {
     if (idx >= P) idx -= P;
-    int found = -1;
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        int i = idx + k;
-        if (i >= P) i -= P;
-        if (found < 0 && v.st[i * v.ld() + s] != ST_BROKEN) found = i;
-    }
-    return found < 0 ? idx : found;
+    const uint32_t alive = all_seats<P>() & ~x.broken;
+    return alive ? first_from(alive, idx) : idx;  // argmax of all-False is 0
 }
 
 // Game.high_bet, game.py:286-290
@@ -111,13 +159,10 @@ PKB_D double high_bet(const V& v, size_t s)
 }
 
 // Game.game_over, game.py:316-320
-template <int P, class V>
-PKB_D bool game_over(const V& v, size_t s)
+template <int P>
+PKB_D bool game_over(const Seats& x)
 {
-    int n = 0;
-#pragma unroll
-    for (int p = 0; p < P; ++p) n += v.st[p * v.ld() + s] != ST_BROKEN;
-    return n == 1;
+    return popc32(all_seats<P>() & ~x.broken) == 1;
 }
 
 // Game.get_valid_actions, game.py:339-383 -> bit a set iff move a is valid
@@ -141,50 +186,44 @@ PKB_D uint32_t valid_mask(const V& v, size_t s, int player)
 // Game.setup_hand, game.py:414-451.  The deck is not materialised: hand `hand` of this episode is
 // a pure function of (seed, env, episode, hand) and is regenerated where it is needed.
 template <int P, class V>
-PKB_D void setup_hand(V& v, size_t s, Meta& m, const GameConst& gc)
+PKB_D void setup_hand(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
 {
     const size_t ld = v.ld();
     v.hand[s] += 1;
     m.turn = 0;
-#pragma unroll
-    for (int p = 0; p < P; ++p)
-        if (v.st[p * ld + s] != ST_BROKEN) v.st[p * ld + s] = ST_ACTIVE;  // :421
-    m.dealer = first_playing<P>(v, s, m.dealer + 1);                      // :432
-    m.sb = first_playing<P>(v, s, m.dealer + 1);                          // :433
-    m.bb = first_playing<P>(v, s, m.sb + 1);                              // :434
-    m.act = first_playing<P>(v, s, m.bb + 1);                             // :435
-#pragma unroll
-    for (int p = 0; p < P; ++p) {  // :438-440; the small blind is written last, so it wins when sb == bb
-        v.bt[p * ld + s] = 0.0;
-        v.pd[p * ld + s] = p == m.sb ? gc.small_blind : p == m.bb ? gc.big_blind : 0.0;
-    }
-    v.st[m.bb * ld + s] = ST_CALLED;  // :441
+    x.active = all_seats<P>() & ~x.broken;  // :421
+    x.called = x.allin = 0;
+    m.dealer = first_playing<P>(x, m.dealer + 1);  // :432
+    m.sb = first_playing<P>(x, m.dealer + 1);      // :433
+    m.bb = first_playing<P>(x, m.sb + 1);          // :434
+    m.act = first_playing<P>(x, m.bb + 1);         // :435
+    set_state(x, m.bb, ST_CALLED);                 // :441
     double hb = 0.0;
 #pragma unroll
-    for (int p = 0; p < P; ++p) {  // :444-446
-        double x = v.pd[p * ld + s];
+    for (int p = 0; p < P; ++p) {  // :438-440 (the small blind is written last, so it wins when sb == bb), :444-446
+        v.bt[p * ld + s] = 0.0;
+        double b = p == m.sb ? gc.small_blind : p == m.bb ? gc.big_blind : 0.0;
         const double c = v.cr[p * ld + s];
-        if (x > c) v.st[p * ld + s] = ST_ALL_IN;
-        if (!(x <= c)) { x = c; v.pd[p * ld + s] = x; }
-        hb = (p == 0 || x > hb) ? x : hb;
+        if (b > c) set_state(x, p, ST_ALL_IN);
+        if (!(b <= c)) b = c;
+        v.pd[p * ld + s] = b;
+        hb = (p == 0 || b > hb) ? b : hb;
     }
     v.mr[s] = hb;
 }
 
 // Game.reset, game.py:397-412 (the episode counter is bumped by the caller)
 template <int P, class V>
-PKB_D void reset_env(V& v, size_t s, Meta& m, const GameConst& gc)
+PKB_D void reset_env(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
 {
     const size_t ld = v.ld();
     m.dealer = gc.dealer;  // :403
     m.act = 0;
     v.hand[s] = 0;
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        v.cr[p * ld + s] = gc.start_credits[p];  // :408
-        v.st[p * ld + s] = ST_ACTIVE;            // :409
-    }
-    setup_hand<P>(v, s, m, gc);
+    for (int p = 0; p < P; ++p) v.cr[p * ld + s] = gc.start_credits[p];  // :408
+    x = Seats{all_seats<P>(), 0, 0, 0};                                  // :409
+    setup_hand<P>(v, s, x, m, gc);
 }
 
 // game.py:457-461 and 554-558
@@ -194,9 +233,9 @@ PKB_D void commit(V& v, size_t s)
     const size_t ld = v.ld();
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        const double x = v.pd[p * ld + s];
-        v.bt[p * ld + s] += x;
-        v.cr[p * ld + s] -= x;
+        const double b = v.pd[p * ld + s];
+        v.bt[p * ld + s] += b;
+        v.cr[p * ld + s] -= b;
         v.pd[p * ld + s] = 0.0;
     }
     v.mr[s] = 0.0;
@@ -204,30 +243,29 @@ PKB_D void commit(V& v, size_t s)
 
 // The betting part of Game.step, game.py:656-696 (the action is already known to be valid)
 template <int P, class V>
-PKB_D void apply_action(V& v, size_t s, int p, int action, const GameConst& gc)
+PKB_D void apply_action(V& v, size_t s, Seats& x, int p, int action, const GameConst& gc)
 {
     const size_t ld = v.ld();
-    if (action == MV_FOLD) v.st[p * ld + s] = ST_FOLDED;        // :656-657
-    else if (action == MV_CHECK) v.st[p * ld + s] = ST_CALLED;  // :659-660
+    if (action == MV_FOLD) set_state(x, p, ST_FOLDED);        // :656-657
+    else if (action == MV_CHECK) set_state(x, p, ST_CALLED);  // :659-660
     else {
-        const double hb = high_bet<P>(v, s);                     // :664
-        double bet = hb >= gc.big_blind ? hb : gc.big_blind;     // :665 max(): first argument on ties
+        const double hb = high_bet<P>(v, s);                   // :664
+        double bet = hb >= gc.big_blind ? hb : gc.big_blind;   // :665 max(): first argument on ties
         const double credit = v.cr[p * ld + s];
-        uint8_t mine = ST_CALLED;                                // :667
-        if (action == MV_ALL_IN) {                               // :669-671
+        int mine = ST_CALLED;                                  // :667
+        if (action == MV_ALL_IN) {                             // :669-671
             bet = credit;
             mine = ST_ALL_IN;
-        } else if (action >= MV_RAISE) {                         // :673-678, three rounded operations
+        } else if (action >= MV_RAISE) {                       // :673-678, three rounded operations
             const double f = action == MV_RAISE ? 0.1 : action == MV_RAISE + 1 ? 0.25 : 0.5;
             bet = __dadd_rn(bet, __dmul_rn(credit - bet, f));
         }
-        if (bet > hb) {  // :680-687
-#pragma unroll
-            for (int i = 0; i < P; ++i)
-                if (v.st[i * ld + s] == ST_CALLED) v.st[i * ld + s] = ST_ACTIVE;
+        if (bet > hb) {  // :680-687 every CALLED seat becomes ACTIVE again, the actor keeps its new state
+            x.active |= x.called;
+            x.called = 0;
             v.mr[s] = bet - hb;
         }
-        v.st[p * ld + s] = mine;
+        set_state(x, p, mine);
         v.pd[p * ld + s] = bet;  // :696
     }
 }
@@ -236,12 +274,12 @@ PKB_D void apply_action(V& v, size_t s, int p, int action, const GameConst& gc)
 //
 // A step is run as a small automaton so that the expensive, rarely taken branches (end_hand and
 // the showdown inside it) can be executed by densely packed threads instead of diverging warps.
-// Control word, one per env slot:
+// Control word, one per parked env:
 //   bits 0-1 pc (0 done, 1 needs end_hand, 2 needs showdown), bit 2 cont (1: end_hand was entered
 //   from next_turn and the seat scan resumes afterwards, game.py:609-611; 0: from the fold path,
 //   game.py:616-619), bits 3-7 current_player of the scan, bits 8-10 the `done` tuple so far,
 //   bits 11-17 next_turn() calls made, bit 18 poisoned, bit 19 invalid action,
-//   bits 20-23 number of potential winners (showdown hand-over between phases)
+//   bits 20-23 number of potential winners (hand-over from end_hand_begin to the showdown)
 struct Ctl {
     int pc, cont, cur, done, nt, poisoned, invalid, npw;
 };
@@ -257,64 +295,65 @@ PKB_D uint32_t pack_ctl(const Ctl& c)
            (uint32_t)c.poisoned << 18 | (uint32_t)c.invalid << 19 | (uint32_t)c.npw << 20;
 }
 
-// The `while` of Game.next_player (game.py:607-611) with next_turn (game.py:541-576) inlined, up to
-// the point where next_turn would call end_hand (turn == 4).
-template <int P, class V>
-PKB_D void seat_scan(V& v, size_t s, Meta& m, Ctl& c)
+// seats act, act+1, .., cur in cyclic order (both < P)
+template <int P>
+PKB_D uint32_t cyclic_interval(int act, int cur)
 {
-    const size_t ld = v.ld();
+    const uint32_t ge_act = all_seats<P>() & ~((1u << act) - 1u), le_cur = (2u << cur) - 1u;
+    return act <= cur ? (ge_act & le_cur) : (ge_act | le_cur);
+}
+
+// The `while` of Game.next_player (game.py:607-611) with next_turn (game.py:541-576) inlined, up to
+// the point where next_turn would call end_hand (turn == 4).  The reference walks seat by seat from
+// active_player until it finds an ACTIVE seat, and calls next_turn when it arrives back at the seat
+// that just acted (`current_player`) without finding one: that is "first ACTIVE seat of the cyclic
+// interval [active_player .. current_player], else next_turn".
+template <int P, class V>
+PKB_D void seat_scan(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
+{
     c.pc = PC_DONE;
-    while (v.st[m.act * ld + s] != ST_ACTIVE) {
-        if (m.act == c.cur) {
-            if (c.nt >= NEXT_TURN_CAP) {  // the reference has no termination guarantee here
-                c.poisoned = 1;
-                return;
-            }
-            ++c.nt;
-            commit<P>(v, s);  // :554-558
-            m.turn += 1;      // :561
-            if (m.turn == 4) {  // :563-565 -> end_hand, then `return game_over, True, True`
-                c.pc = PC_END_HAND;
-                c.cont = 1;
-                return;
-            }
-            int called = 0;
-#pragma unroll
-            for (int p = 0; p < P; ++p) called += v.st[p * ld + s] == ST_CALLED;
-            if (called > 1) {  // :570-572
-#pragma unroll
-                for (int p = 0; p < P; ++p)
-                    if (v.st[p * ld + s] == ST_CALLED) v.st[p * ld + s] = ST_ACTIVE;
-            }
-            m.act = first_playing<P>(v, s, m.dealer + 1);  // :575
-            c.done = (int)F_ROUND_OVER;                    // :576
-        } else {
-            m.act = m.act + 1 == P ? 0 : m.act + 1;  // :611
+    for (;;) {
+        const uint32_t cand = x.active & cyclic_interval<P>(m.act, c.cur);
+        if (cand) {
+            m.act = first_from(cand, m.act);
+            return;
         }
+        m.act = c.cur;
+        if (c.nt >= NEXT_TURN_CAP) {  // the reference has no termination guarantee here
+            c.poisoned = 1;
+            return;
+        }
+        ++c.nt;
+        commit<P>(v, s);  // :554-558
+        m.turn += 1;      // :561
+        if (m.turn == 4) {  // :563-565 -> end_hand, then `return game_over, True, True`
+            c.pc = PC_END_HAND;
+            c.cont = 1;
+            return;
+        }
+        if (popc32(x.called) > 1) {  // :567-572
+            x.active |= x.called;
+            x.called = 0;
+        }
+        m.act = first_playing<P>(x, m.dealer + 1);  // :575
+        c.done = (int)F_ROUND_OVER;                 // :576
     }
 }
 
 // Game.step up to the first end_hand (game.py:648-699 and 597-605)
 template <int P, class V>
-PKB_D void step_begin(V& v, size_t s, Meta& m, Ctl& c, int action, uint32_t vmask, const GameConst& gc)
+PKB_D void step_begin(V& v, size_t s, Seats& x, Meta& m, Ctl& c, int action, uint32_t vmask, const GameConst& gc)
 {
-    const size_t ld = v.ld();
     c = Ctl{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
     if (action < 0 || action >= NUM_MOVES || !(vmask >> action & 1u)) {  // :648-651, before any mutation
         c.invalid = 1;
         return;
     }
-    apply_action<P>(v, s, m.act, action, gc);
-    int playing = 0;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const int st = v.st[p * ld + s];
-        playing += st != ST_BROKEN && st != ST_FOLDED;  // :598-599
-    }
-    if (playing > 1) {  // :601-605
+    apply_action<P>(v, s, x, m.act, action, gc);
+    if (popc32(x.active | x.called | x.allin) > 1) {  // :598-605
         c.cur = m.act;
         m.act = m.act + 1 == P ? 0 : m.act + 1;
-        seat_scan<P>(v, s, m, c);
+        seat_scan<P>(v, s, x, m, c);
     } else {  // :616-619
         c.pc = PC_END_HAND;
         c.cont = 0;
@@ -326,25 +365,19 @@ PKB_D void step_begin(V& v, size_t s, Meta& m, Ctl& c, int action, uint32_t vmas
 // From here until setup_hand the PENDING plane carries self.payoffs (it is all zero after commit and
 // is rewritten by the next setup_hand), so no per-seat register array crosses a phase boundary.
 template <int P, class V>
-PKB_D bool end_hand_begin(V& v, size_t s, Ctl& c)
+PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c)
 {
     const size_t ld = v.ld();
     commit<P>(v, s);  // :457-461; pending (= payoffs from here on) is now 0.0, :468
-    int n = 0, first = -1;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const int st = v.st[p * ld + s];
-        if (st != ST_BROKEN && st != ST_FOLDED) {  // :471
-            if (first < 0) first = p;
-            ++n;
-        }
-    }
+    const uint32_t contenders = x.active | x.called | x.allin;  // :471 not BROKEN, not FOLDED
+    const int n = popc32(contenders);
     c.npw = n;
     if (n == 0) {  // :473 -- AssertionError in the reference
         c.poisoned = 1;
         return false;
     }
     if (n == 1) {  // :475-482
+        const int first = __ffs((int)contenders) - 1;
         const double pot = sum_plane<P>(v, v.bt, s);
         v.pd[first * ld + s] = pot;
         v.cr[first * ld + s] += pot;
@@ -353,16 +386,16 @@ PKB_D bool end_hand_begin(V& v, size_t s, Ctl& c)
     return true;
 }
 
-// Game.end_hand, ranked showdown (game.py:483-528).  `rank7(mask)` evaluates a 7-card id mask
-// (eval_mask52, possibly out of line).  The working copy of bets is kept in registers; payoffs
-// are written to the pending plane at the end.
+// Game.end_hand, ranked showdown (game.py:483-528).  `rank7(mask)` evaluates a 7-card id mask.
+// The working copy of bets is kept in registers; payoffs are written to the pending plane at the end.
 template <int P, class V, class Rank7>
-PKB_D void showdown(V& v, size_t s, const Ctl& c, uint64_t seed, uint32_t env_id, uint32_t episode, Rank7 rank7)
+PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed, uint32_t env_id, uint32_t episode,
+                    Rank7 rank7)
 {
     const size_t ld = v.ld();
     uint32_t rk[P];
     double b[P], pay[P];
-    uint32_t todo = 0;
+    uint32_t todo = x.called | x.allin;  // :488, :496 seats that show their cards
     {  // :488-489 eval_hand(board + hole) for CALLED / ALL_IN seats, NONE for the others
         Dealer d(seed, env_id, episode, v.hand[s]);
         uint64_t board = 0;
@@ -371,10 +404,7 @@ PKB_D void showdown(V& v, size_t s, const Ctl& c, uint64_t seed, uint32_t env_id
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const uint64_t hole = (1ull << d.next()) | (1ull << d.next());
-            const int st = v.st[p * ld + s];
-            const bool shows = st == ST_CALLED || st == ST_ALL_IN;
-            rk[p] = shows ? rank7(board | hole) : PACKED_NONE;
-            todo |= (uint32_t)shows << p;
+            rk[p] = (todo >> p & 1u) ? rank7(board | hole) : PACKED_NONE;
             b[p] = v.bt[p * ld + s];  // :485 working copy
             pay[p] = 0.0;
         }
@@ -386,8 +416,8 @@ PKB_D void showdown(V& v, size_t s, const Ctl& c, uint64_t seed, uint32_t env_id
         bool have = false;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            const double x = v.bt[i * ld + s];
-            if ((todo >> i & 1u) && (!have || x < least)) { p = i; least = x; have = true; }
+            const double bi = v.bt[i * ld + s];
+            if ((todo >> i & 1u) && (!have || bi < least)) { p = i; least = bi; have = true; }
         }
         todo &= ~(1u << p);
         bool nothing_left = true;
@@ -408,8 +438,8 @@ PKB_D void showdown(V& v, size_t s, const Ctl& c, uint64_t seed, uint32_t env_id
         double layer[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) {  // :509 np.clip(bets, 0, max_bet)
-            const double x = b[i] < 0.0 ? 0.0 : b[i];
-            layer[i] = x > max_bet ? max_bet : x;
+            const double bi = b[i] < 0.0 ? 0.0 : b[i];
+            layer[i] = bi > max_bet ? max_bet : bi;
         }
         WinnerScan ws;  // :512
 #pragma unroll
@@ -440,11 +470,10 @@ PKB_D void showdown(V& v, size_t s, const Ctl& c, uint64_t seed, uint32_t env_id
 }
 
 // Game.end_hand, last part (game.py:530-539), then what the caller of end_hand does with its
-// return value (game.py:565 / 609-611 or game.py:619).  `deal(m)` runs setup_hand (possibly out of
-// line) and returns the new Meta; `pay_out` receives the hand's final payoffs.
-template <int P, class V, class Deal>
-PKB_D void end_hand_finish(V& v, size_t s, Meta& m, Ctl& c, double* payoffs_out, size_t out_ld, size_t out_idx,
-                           double (&pay_out)[P], Deal deal)
+// return value (game.py:565 / 609-611 or game.py:619).  `pay_out` receives the hand's final payoffs.
+template <int P, class V>
+PKB_D void end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* payoffs_out, size_t out_ld, size_t out_idx,
+                           double (&pay_out)[P], const GameConst& gc)
 {
     const size_t ld = v.ld();
 #pragma unroll
@@ -452,14 +481,14 @@ PKB_D void end_hand_finish(V& v, size_t s, Meta& m, Ctl& c, double* payoffs_out,
         const double pay = v.pd[p * ld + s] - v.bt[p * ld + s];  // :531
         pay_out[p] = pay;
         payoffs_out[p * out_ld + out_idx] = pay;
-        if (v.cr[p * ld + s] <= 0.0) v.st[p * ld + s] = ST_BROKEN;  // :536
+        if (v.cr[p * ld + s] <= 0.0) set_state(x, p, ST_BROKEN);  // :536
     }
-    m = deal(m);  // :539 setup_hand -- runs even when the game is over
-    const int over = game_over<P>(v, s) ? (int)F_GAME_OVER : 0;
+    setup_hand<P>(v, s, x, m, gc);  // :539 -- runs even when the game is over
+    const int over = game_over<P>(x) ? (int)F_GAME_OVER : 0;
     if (c.cont) {  // next_turn: `return self.game_over, True, True`, then the scan goes on (:609-611)
         c.done = over | (int)(F_HAND_OVER | F_ROUND_OVER);
         if (over) c.pc = PC_DONE;
-        else seat_scan<P>(v, s, m, c);
+        else seat_scan<P>(v, s, x, m, c);
     } else {  // :619
         c.done = over | (int)F_HAND_OVER;
         c.pc = PC_DONE;

@@ -85,34 +85,37 @@ PKB_D View<STEP_THREADS> carve_view(unsigned char* smem)
     return v;
 }
 
+// HBM planes -> the thread's staging slot; the seat states come back as masks (registers)
 template <int P>
-PKB_D void load_env(View<STEP_THREADS>& v, int t, const DevState& d, size_t env)
+PKB_D Seats load_env(View<STEP_THREADS>& v, int t, const DevState& d, size_t env)
 {
+    const View<0> g = global_view(d);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         v.cr[p * STEP_THREADS + t] = d.cr[p * d.stride + env];
         v.bt[p * STEP_THREADS + t] = d.bt[p * d.stride + env];
         v.pd[p * STEP_THREADS + t] = d.pd[p * d.stride + env];
-        v.st[p * STEP_THREADS + t] = d.st[p * d.stride + env];
     }
     v.mr[t] = d.mr[env];
     v.meta[t] = d.meta[env];
     v.hand[t] = d.hand[env];
+    return load_seats<P>(g, env);
 }
 
 template <int P>
-PKB_D void store_env(const View<STEP_THREADS>& v, int t, const DevState& d, size_t env)
+PKB_D void store_env(const View<STEP_THREADS>& v, int t, const Seats& x, const DevState& d, size_t env)
 {
+    View<0> g = global_view(d);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         d.cr[p * d.stride + env] = v.cr[p * STEP_THREADS + t];
         d.bt[p * d.stride + env] = v.bt[p * STEP_THREADS + t];
         d.pd[p * d.stride + env] = v.pd[p * STEP_THREADS + t];
-        d.st[p * d.stride + env] = v.st[p * STEP_THREADS + t];
     }
     d.mr[env] = v.mr[t];
     d.meta[env] = v.meta[t];
     d.hand[env] = v.hand[t];
+    store_seats<P>(g, env, x);
 }
 
 // warp-aggregated append of env ids to a work list
@@ -148,30 +151,28 @@ PKB_D uint32_t write_outputs(const View<STEP_THREADS>& v, int t, const Ctl& c, c
 // caller's use of the return value), then Game.reset() if the game ended and auto-reset is on.
 // Leaves c.pc == PC_END_HAND when ANOTHER hand ends inside the same step (rare: all-in blinds).
 template <int P>
-PKB_D void finish_hand(View<STEP_THREADS>& v, int t, Meta& m, Ctl& c, const StepArgs& a, size_t env, double (&paysum)[P])
+PKB_D void finish_hand(View<STEP_THREADS>& v, int t, Seats& x, Meta& m, Ctl& c, const StepArgs& a, size_t env,
+                       double (&paysum)[P])
 {
     const DevState& d = a.d;
     double pay[P];
-    end_hand_finish<P>(v, t, m, c, d.payoffs, d.stride, env, pay, [&](Meta mm) {
-        setup_hand<P>(v, t, mm, a.gc);
-        return mm;
-    });
+    end_hand_finish<P>(v, t, x, m, c, d.payoffs, d.stride, env, pay, a.gc);
 #pragma unroll
     for (int p = 0; p < P; ++p) paysum[p] += pay[p];
     if (c.pc == PC_DONE && (c.done & (int)F_GAME_OVER) && !c.poisoned && a.gc.auto_reset) {
         d.episode[env] += 1;  // Game.reset() right after the step that ended the game (game.py:397-412)
-        reset_env<P>(v, t, m, a.gc);
+        reset_env<P>(v, t, x, m, a.gc);
     }
 }
 
 // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
 // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED.
 template <int P>
-PKB_D void assert_exit(const View<STEP_THREADS>& v, int t, Ctl& c, const StepArgs& a, size_t env)
+PKB_D void assert_exit(const Seats& x, Ctl& c, const StepArgs& a, size_t env)
 {
 #pragma unroll
     for (int p = 0; p < P; ++p) a.d.payoffs[p * a.d.stride + env] = 0.0;
-    c.done = c.cont ? (int)((game_over<P>(v, t) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
+    c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
     c.pc = PC_DONE;
 }
 
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_a(const __grid_const
     const bool live = env < d.n;
     if (blockIdx.x == 0 && t < 2) d.counters[2 * (a.parity ^ 1u) + t] = 0;  // next step's list lengths
 
-    load_env<P>(v, t, d, env);  // stride is a multiple of the block size: always in bounds
+    Seats x = load_env<P>(v, t, d, env);  // stride is a multiple of the block size: always in bounds
     Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
         Meta m = unpack_meta(v.meta[t]);
@@ -242,12 +243,12 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_a(const __grid_const
             if (a.actions_out) a.actions_out[env] = action;
         } else
             action = a.actions[env];
-        step_begin<P>(v, t, m, c, action, vm, a.gc);
+        step_begin<P>(v, t, x, m, c, action, vm, a.gc);
         v.meta[t] = pack_meta(m);
     }
     const bool parked = live && c.pc == PC_END_HAND;
     if (live) {
-        if (!c.invalid) store_env<P>(v, t, d, env);  // an invalid action changes nothing (game.py:649-651)
+        if (!c.invalid) store_env<P>(v, t, x, d, env);  // an invalid action changes nothing (game.py:649-651)
         if (parked) d.ctl[env] = pack_ctl(c);
         else write_outputs<P>(v, t, c, a, env);
     }
@@ -279,20 +280,20 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_b(const __grid_const
         size_t env = 0;
         if (active) {
             env = d.list_e[i];
-            load_env<P>(v, t, d, env);
+            Seats x = load_env<P>(v, t, d, env);
             Ctl c = unpack_ctl(d.ctl[env]);
             Meta m = unpack_meta(v.meta[t]);
-            if (end_hand_begin<P>(v, t, c)) {
+            if (end_hand_begin<P>(v, t, x, c)) {
                 c.pc = PC_SHOWDOWN;
                 to_c = true;
             } else if (c.poisoned) {
-                assert_exit<P>(v, t, c, a, env);
+                assert_exit<P>(x, c, a, env);
             } else {
-                finish_hand<P>(v, t, m, c, a, env, paysum);
+                finish_hand<P>(v, t, x, m, c, a, env, paysum);
                 to_c = c.pc == PC_END_HAND;  // another hand ends inside this step: kernel C runs it
             }
             v.meta[t] = pack_meta(m);
-            store_env<P>(v, t, d, env);
+            store_env<P>(v, t, x, d, env);
             if (to_c) d.ctl[env] = pack_ctl(c);
             else {
                 const uint32_t f = write_outputs<P>(v, t, c, a, env);
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_c(const __grid_const
     for (int p = 0; p < P; ++p) paysum[p] = 0.0;
     for (uint32_t i = blockIdx.x * STEP_THREADS + t; i < n_items; i += gridDim.x * STEP_THREADS) {
         const size_t env = d.list_s[i];
-        load_env<P>(v, t, d, env);
+        Seats x = load_env<P>(v, t, d, env);
         Ctl c = unpack_ctl(d.ctl[env]);
         Meta m = unpack_meta(v.meta[t]);
         const uint32_t episode = d.episode[env];
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_c(const __grid_const
             bool ranked = c.pc == PC_SHOWDOWN;
             if (!ranked) {  // PC_END_HAND: a further hand of this step, from its beginning
                 ++hands;
-                ranked = end_hand_begin<P>(v, t, c);
+                ranked = end_hand_begin<P>(v, t, x, c);
                 if (!ranked && c.poisoned) {
                     asserted = true;
                     break;
@@ -340,15 +341,15 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_c(const __grid_const
             }
             if (ranked) {
                 ++shows;
-                showdown<P>(v, t, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode,
+                showdown<P>(v, t, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode,
                             [](uint64_t mask) { return eval_mask52(mask); });
             }
             c.pc = PC_DONE;
-            finish_hand<P>(v, t, m, c, a, env, paysum);
+            finish_hand<P>(v, t, x, m, c, a, env, paysum);
         }
-        if (asserted) assert_exit<P>(v, t, c, a, env);
+        if (asserted) assert_exit<P>(x, c, a, env);
         v.meta[t] = pack_meta(m);
-        store_env<P>(v, t, d, env);
+        store_env<P>(v, t, x, d, env);
         const uint32_t f = write_outputs<P>(v, t, c, a, env);
         games += (f & F_GAME_OVER) ? 1u : 0u;
         poisoned += c.poisoned ? 1u : 0u;
@@ -367,7 +368,9 @@ __global__ void reset_kernel(DevState d, GameConst gc, const uint8_t* mask)
     View<0> v = global_view(d);
     d.episode[env] += 1;
     Meta m = unpack_meta(d.meta[env]);
-    reset_env<P>(v, env, m, gc);
+    Seats x{0, 0, 0, 0};
+    reset_env<P>(v, env, x, m, gc);
+    store_seats<P>(v, env, x);
     d.meta[env] = pack_meta(m);
 }
 
@@ -386,7 +389,7 @@ __global__ void game_over_kernel(DevState d, uint8_t* out)
 {
     const size_t env = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= d.n) return;
-    out[env] = game_over<P>(global_view(d), env) ? 1 : 0;
+    out[env] = game_over<P>(load_seats<P>(global_view(d), env)) ? 1 : 0;
 }
 
 // K5: RandomAgent (agents/random.py:16-17) / weighted mix over the valid mask
