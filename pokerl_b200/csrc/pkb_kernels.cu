@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -49,10 +50,20 @@ struct StepArgs {
     uint32_t use_weights;
     uint32_t weights[NUM_MOVES];
     uint32_t parity;  // which pair of list counters this step uses; the other pair is zeroed for the next step
+    // the slice of the handle's envs this launch works on (slices run concurrently on internal streams)
+    uint32_t env_lo, env_cnt;  // first local env, number of env slots (a multiple of the block size)
+    uint32_t* list_e;          // [env_cnt] work list of kernel B
+    uint32_t* list_s;          // [env_cnt] work list of kernel C
+    uint32_t* counters;        // [4] list lengths: {e, s} x step parity
 };
 
 constexpr int TILE = 256;         // env-count granularity of the HBM planes (stride is a multiple of it)
 constexpr int STEP_THREADS = 128; // block size of the three step kernels (one env per thread)
+constexpr int MAX_SLICES = 16;    // env slices of one handle that may be stepped concurrently
+#ifndef PKB_BC_MIN_BLOCKS
+#define PKB_BC_MIN_BLOCKS 4
+#endif
+constexpr int BC_MIN_BLOCKS = PKB_BC_MIN_BLOCKS;  // resident blocks/SM kernels B and C are compiled for (register cap)
 
 // bytes of shared memory per thread-slot: f64 planes (3P+1), meta/hand u32, P state bytes
 template <int P>
@@ -118,16 +129,28 @@ PKB_D void store_env(const View<STEP_THREADS>& v, int t, const Seats& x, const D
     store_seats<P>(g, env, x);
 }
 
-// warp-aggregated append of env ids to a work list
+// block-aggregated append of env ids to a work list: one global atomic per block, entries in
+// thread order.  Must be reached by every thread of the block.
 PKB_D void list_append(uint32_t* list, uint32_t* counter, bool mine, uint32_t env)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_warp[STEP_THREADS / 32], s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned vote = __ballot_sync(0xffffffffu, mine);
-    if (!vote) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(vote));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (mine) list[base + __popc(vote & ((1u << lane) - 1u))] = env;
+    if (lane == 0) s_warp[wid] = (uint32_t)__popc(vote);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int i = 0; i < STEP_THREADS / 32; ++i) total += s_warp[i];
+        s_base = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    if (mine) {
+        uint32_t at = s_base + (uint32_t)__popc(vote & ((1u << lane) - 1u));
+        for (int i = 0; i < wid; ++i) at += s_warp[i];
+        list[at] = env;
+    }
+    __syncthreads();  // s_warp / s_base are reused by the next call
 }
 
 // warp-aggregated event counter -> one global atomic per warp that saw the event
@@ -227,9 +250,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_a(const __grid_const
     View<STEP_THREADS> v = carve_view<P>(smem_raw);
     const DevState& d = a.d;
     const int t = threadIdx.x;
-    const size_t env = (size_t)blockIdx.x * STEP_THREADS + t;
+    const size_t env = (size_t)a.env_lo + (size_t)blockIdx.x * STEP_THREADS + t;
     const bool live = env < d.n;
-    if (blockIdx.x == 0 && t < 2) d.counters[2 * (a.parity ^ 1u) + t] = 0;  // next step's list lengths
+    if (blockIdx.x == 0 && t < 2) a.counters[2 * (a.parity ^ 1u) + t] = 0;  // next step's list lengths
 
     Seats x = load_env<P>(v, t, d, env);  // stride is a multiple of the block size: always in bounds
     Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
@@ -252,23 +275,26 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_a(const __grid_const
         if (parked) d.ctl[env] = pack_ctl(c);
         else write_outputs<P>(v, t, c, a, env);
     }
-    list_append(d.list_e, &d.counters[2 * a.parity], parked, (uint32_t)env);
+    list_append(a.list_e, &a.counters[2 * a.parity], parked, (uint32_t)env);
     if (a.gc.track_stats) {
         count_events(&d.stats[STAT_INVALID], live && c.invalid);
         count_events(&d.stats[STAT_POISONED], live && c.poisoned);
-        if (blockIdx.x == 0 && t == 0) atomicAdd(&d.stats[STAT_STEPS], (unsigned long long)d.n);  // minus invalid: see pkb_stats
+        if (blockIdx.x == 0 && t == 0) {  // live envs of this slice; pkb_stats subtracts the invalid ones
+            const size_t hi = (size_t)a.env_lo + a.env_cnt;
+            atomicAdd(&d.stats[STAT_STEPS], (unsigned long long)((hi < d.n ? hi : d.n) - a.env_lo));
+        }
     }
 }
 
 // K2a: end_hand for the envs in list E
 template <int P>
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel_b(const __grid_constant__ StepArgs a)
+__global__ void __launch_bounds__(STEP_THREADS, BC_MIN_BLOCKS) step_kernel_b(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     View<STEP_THREADS> v = carve_view<P>(smem_raw);
     const DevState& d = a.d;
     const int t = threadIdx.x;
-    const uint32_t n_items = d.counters[2 * a.parity];
+    const uint32_t n_items = a.counters[2 * a.parity];
     uint32_t games = 0, poisoned = 0;
     double paysum[P];
 #pragma unroll
@@ -279,7 +305,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_b(const __grid_const
         bool to_c = false;
         size_t env = 0;
         if (active) {
-            env = d.list_e[i];
+            env = a.list_e[i];
             Seats x = load_env<P>(v, t, d, env);
             Ctl c = unpack_ctl(d.ctl[env]);
             Meta m = unpack_meta(v.meta[t]);
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_b(const __grid_const
                 poisoned += c.poisoned ? 1u : 0u;
             }
         }
-        list_append(d.list_s, &d.counters[2 * a.parity + 1], to_c, (uint32_t)env);
+        list_append(a.list_s, &a.counters[2 * a.parity + 1], to_c, (uint32_t)env);
     }
     if (a.gc.track_stats) {
         const uint32_t hands = (blockIdx.x == 0 && t == 0) ? n_items : 0u;
@@ -311,19 +337,19 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_b(const __grid_const
 
 // K2b: ranked showdowns (and the rare further hands of a step) for the envs in list S
 template <int P>
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel_c(const __grid_constant__ StepArgs a)
+__global__ void __launch_bounds__(STEP_THREADS, BC_MIN_BLOCKS) step_kernel_c(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     View<STEP_THREADS> v = carve_view<P>(smem_raw);
     const DevState& d = a.d;
     const int t = threadIdx.x;
-    const uint32_t n_items = d.counters[2 * a.parity + 1];
+    const uint32_t n_items = a.counters[2 * a.parity + 1];
     uint32_t hands = 0, shows = 0, games = 0, poisoned = 0;
     double paysum[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) paysum[p] = 0.0;
     for (uint32_t i = blockIdx.x * STEP_THREADS + t; i < n_items; i += gridDim.x * STEP_THREADS) {
-        const size_t env = d.list_s[i];
+        const size_t env = a.list_s[i];
         Seats x = load_env<P>(v, t, d, env);
         Ctl c = unpack_ctl(d.ctl[env]);
         Meta m = unpack_meta(v.meta[t]);
@@ -569,9 +595,20 @@ struct pkb_env {
     size_t arena_bytes;
     uint32_t* d_weights;
     uint32_t parity;  // step parity: which pair of list counters the next step uses
+    // env slices stepped concurrently on internal streams (fork/join around the caller's stream)
+    int num_slices;
+    cudaStream_t streams[MAX_SLICES];
+    cudaEvent_t fork, join[MAX_SLICES];
 };
 
 static thread_local std::string g_error;
+
+static int slices_from_env()
+{
+    const char* e = getenv("PKB_SLICES");
+    int n = e ? atoi(e) : 1;
+    return n < 1 ? 1 : (n > MAX_SLICES ? MAX_SLICES : n);
+}
 
 static int fail(const char* what, cudaError_t e = cudaSuccess)
 {
@@ -618,13 +655,14 @@ static cudaError_t launch_step(const StepArgs& a, cudaStream_t s)
         e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
     }
-    const unsigned blocks_a = (unsigned)(a.d.stride / STEP_THREADS);
-    // B and C read their item count on the device; a few waves of blocks walk the list with a grid stride
-    const unsigned cap = (unsigned)sm_count[dev] * 8u;
-    const unsigned blocks_bc = blocks_a < cap ? blocks_a : cap;
+    const unsigned blocks_a = a.env_cnt / STEP_THREADS;
+    // B and C read their item count on the device.  Their grids cover the usual share of envs whose
+    // hand ends (about 1/3) / is ranked (about 1/8) in one pass, so that all items are in flight at
+    // once; a grid stride handles anything beyond that, and surplus blocks exit at once.
+    const unsigned blocks_b = blocks_a / 2 + 1, blocks_c = blocks_a / 4 + 1;
     step_kernel_a<P, SAMPLE><<<blocks_a, STEP_THREADS, smem, s>>>(a);
-    step_kernel_b<P><<<blocks_bc, STEP_THREADS, smem, s>>>(a);
-    step_kernel_c<P><<<blocks_bc, STEP_THREADS, smem, s>>>(a);
+    step_kernel_b<P><<<blocks_b, STEP_THREADS, smem, s>>>(a);
+    step_kernel_c<P><<<blocks_c, STEP_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -661,7 +699,7 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     // arena: f64 planes | u32 planes | u8 planes | stats
     const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)6 * stride, n_u8 = (size_t)P * stride;
     const size_t off_u32 = n_f64 * 8, off_u8 = off_u32 + n_u32 * 4, off_stats = (off_u8 + n_u8 + 255) / 256 * 256;
-    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 4 * 4;
+    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 4 * 4 * MAX_SLICES;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) {
         delete h;
@@ -706,6 +744,21 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     gc.dealer = cfg->dealer;
     gc.auto_reset = cfg->auto_reset;
     gc.track_stats = 1;
+    // slices: at least 64 blocks each, so small batches stay on the caller's stream
+    h->num_slices = slices_from_env();
+    while (h->num_slices > 1 && stride / h->num_slices < 64 * STEP_THREADS) --h->num_slices;
+    if (h->num_slices > 1) {
+        e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
+        for (int i = 0; i < h->num_slices && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) {
+            cudaFree(h->arena);
+            delete h;
+            return fail("pkb_create: streams", e);
+        }
+    }
     *out = h;
     return 0;
 }
@@ -714,6 +767,14 @@ int pkb_destroy(pkb_env* h)
 {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
+    if (h->num_slices > 1) {
+        for (int i = 0; i < h->num_slices; ++i) {
+            cudaStreamSynchronize(h->streams[i]);
+            cudaStreamDestroy(h->streams[i]);
+            cudaEventDestroy(h->join[i]);
+        }
+        cudaEventDestroy(h->fork);
+    }
     cudaFree(h->arena);
     delete h;
     return 0;
@@ -756,11 +817,30 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.parity = h->parity;
     h->parity ^= 1u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaSuccess;
-    PKB_DISPATCH_P(h->cfg.num_players,
-                   e = sample ? launch_step<P, true>(a, s) : launch_step<P, false>(a, s));
-    if (e != cudaSuccess) return fail("pkb_step: launch", e);
+    cudaStream_t caller = static_cast<cudaStream_t>(stream);
+    const int S = h->num_slices;
+    // slice boundaries on multiples of the block size
+    const uint64_t blocks = h->d.stride / STEP_THREADS, per = (blocks + S - 1) / S;
+    if (S > 1) PKB_CUDA(cudaEventRecord(h->fork, caller));
+    for (int i = 0; i < S; ++i) {
+        const uint64_t b0 = per * i, b1 = b0 + per < blocks ? b0 + per : blocks;
+        if (b0 >= b1) continue;
+        a.env_lo = (uint32_t)(b0 * STEP_THREADS);
+        a.env_cnt = (uint32_t)((b1 - b0) * STEP_THREADS);
+        a.list_e = h->d.list_e + a.env_lo;
+        a.list_s = h->d.list_s + a.env_lo;
+        a.counters = h->d.counters + 4 * i;
+        cudaStream_t s = S > 1 ? h->streams[i] : caller;
+        if (S > 1) PKB_CUDA(cudaStreamWaitEvent(s, h->fork, 0));
+        cudaError_t e = cudaSuccess;
+        PKB_DISPATCH_P(h->cfg.num_players,
+                       e = sample ? launch_step<P, true>(a, s) : launch_step<P, false>(a, s));
+        if (e != cudaSuccess) return fail("pkb_step: launch", e);
+        if (S > 1) {
+            PKB_CUDA(cudaEventRecord(h->join[i], s));
+            PKB_CUDA(cudaStreamWaitEvent(caller, h->join[i], 0));
+        }
+    }
     return 0;
 }
 

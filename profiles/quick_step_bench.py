@@ -31,9 +31,17 @@ for i, (a, b) in enumerate(ev):
     g.step_random(32 + i, w)
     b.record()
 torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for i in range(args.steps):
+    g.step_random(1000 + i, w)
+t_issue = time.perf_counter() - t0
+torch.cuda.synchronize()
+t_wall = time.perf_counter() - t0
 ms = sorted(a.elapsed_time(b) for a, b in ev)
 mean = sum(ms) / len(ms)
 B = 2 * (25 * args.players + 20) + 6
+print(f"slices={os.environ.get('PKB_SLICES', '1')} back-to-back (no flush): host issue {t_issue/args.steps*1e6:.1f}us/step, wall {t_wall/args.steps*1e6:.1f}us/step")
 print(f"lib={os.environ.get('PKB_LIB', 'default')} P={args.players} N={args.envs} mean={mean*1e3:.1f}us median={ms[len(ms)//2]*1e3:.1f}us "
       f"min={ms[0]*1e3:.1f}us  {args.envs/mean/1e6:.2f} G env-steps/s  {B*args.envs/mean/1e6:.0f} GB/s algorithmic "
       f"({B*args.envs/mean/1e6/6543.4:.3f} of 6543.4)")
