@@ -323,7 +323,7 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N,
                 "d2h_bytes_per_step": 2 * N, "steps": E,
                 "path": "GameBatch.step(actions from pinned host) -> pkb_step -> flags+valid to pinned host, sync per step"},
-        "gpu_launches": K,
+        "gpu_launches": 3 * K,  # step_kernel_a/b/c per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world * K / (resident_ms / 1e3), "unit": "env-steps/s",
                         "note": "same K steps back to back without the L2 flush (state stays in the 126 MB L2)"},
