@@ -166,21 +166,25 @@ PKB_D bool game_over(const Seats& x)
 }
 
 // Game.get_valid_actions, game.py:339-383 -> bit a set iff move a is valid
-template <int P, class V>
-PKB_D uint32_t valid_mask(const V& v, size_t s, int player)
+PKB_D uint32_t valid_mask_from(double hb, double credit, double mr)
 {
-    const double hb = high_bet<P>(v, s), credit = v.cr[player * v.ld() + s], mr = v.mr[s];
     const double room = credit - hb;
     uint32_t m = 1u << MV_FOLD | 1u << MV_ALL_IN;  // :367
     const double f[3] = {0.1, 0.25, 0.5};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {  // :370-372, product and sum rounded separately
         const double rv = __dmul_rn(f[i], room);
-        if (rv > mr && __dadd_rn(hb, rv) < credit) m |= 1u << (MV_RAISE + i);
+        m |= (uint32_t)(rv > mr && __dadd_rn(hb, rv) < credit) << (MV_RAISE + i);
     }
-    if (hb == 0.0) m |= 1u << MV_CHECK;    // :375
-    if (hb < credit) m |= 1u << MV_CALL;   // :376
+    m |= (uint32_t)(hb == 0.0) << MV_CHECK;   // :375
+    m |= (uint32_t)(hb < credit) << MV_CALL;  // :376
     return m;
+}
+
+template <int P, class V>
+PKB_D uint32_t valid_mask(const V& v, size_t s, int player)
+{
+    return valid_mask_from(high_bet<P>(v, s), v.cr[player * v.ld() + s], v.mr[s]);
 }
 
 // Game.setup_hand, game.py:414-451.  The deck is not materialised: hand `hand` of this episode is
@@ -241,33 +245,24 @@ PKB_D void commit(V& v, size_t s)
     v.mr[s] = 0.0;
 }
 
-// The betting part of Game.step, game.py:656-696 (the action is already known to be valid)
+// The betting part of Game.step, game.py:656-696 (the action is already known to be valid), written
+// as selects so that the 32 envs of a warp do not diverge on the move.  `hb` = high_bet, `credit` =
+// credits[p] (both already read for the valid mask).
 template <int P, class V>
-PKB_D void apply_action(V& v, size_t s, Seats& x, int p, int action, const GameConst& gc)
+PKB_D void apply_action(V& v, size_t s, Seats& x, int p, int action, double hb, double credit, const GameConst& gc)
 {
-    const size_t ld = v.ld();
-    if (action == MV_FOLD) set_state(x, p, ST_FOLDED);        // :656-657
-    else if (action == MV_CHECK) set_state(x, p, ST_CALLED);  // :659-660
-    else {
-        const double hb = high_bet<P>(v, s);                   // :664
-        double bet = hb >= gc.big_blind ? hb : gc.big_blind;   // :665 max(): first argument on ties
-        const double credit = v.cr[p * ld + s];
-        int mine = ST_CALLED;                                  // :667
-        if (action == MV_ALL_IN) {                             // :669-671
-            bet = credit;
-            mine = ST_ALL_IN;
-        } else if (action >= MV_RAISE) {                       // :673-678, three rounded operations
-            const double f = action == MV_RAISE ? 0.1 : action == MV_RAISE + 1 ? 0.25 : 0.5;
-            bet = __dadd_rn(bet, __dmul_rn(credit - bet, f));
-        }
-        if (bet > hb) {  // :680-687 every CALLED seat becomes ACTIVE again, the actor keeps its new state
-            x.active |= x.called;
-            x.called = 0;
-            v.mr[s] = bet - hb;
-        }
-        set_state(x, p, mine);
-        v.pd[p * ld + s] = bet;  // :696
+    const bool bets = action >= MV_CALL;                                       // :662 (FOLD :656, CHECK :659 bet nothing)
+    const double base = hb >= gc.big_blind ? hb : gc.big_blind;                // :665 max(): first argument on ties
+    const double f = action == MV_RAISE ? 0.1 : action == MV_RAISE + 1 ? 0.25 : 0.5;
+    const double raised = __dadd_rn(base, __dmul_rn(credit - base, f));        // :673-678, three rounded operations
+    const double bet = action == MV_ALL_IN ? credit : action >= MV_RAISE ? raised : base;  // :669-671
+    if (bets && bet > hb) {  // :680-687 every CALLED seat becomes ACTIVE again, the actor keeps its new state
+        x.active |= x.called;
+        x.called = 0;
+        v.mr[s] = bet - hb;
     }
+    set_state(x, p, action == MV_FOLD ? ST_FOLDED : action == MV_ALL_IN ? ST_ALL_IN : ST_CALLED);  // :657, :660, :667, :671
+    if (bets) v.pd[p * v.ld() + s] = bet;  // :696
 }
 
 // ---- the resumable part of Game.next_player / next_turn / end_hand ------------------------------
@@ -303,53 +298,81 @@ PKB_D uint32_t cyclic_interval(int act, int cur)
     return act <= cur ? (ge_act & le_cur) : (ge_act | le_cur);
 }
 
-// The `while` of Game.next_player (game.py:607-611) with next_turn (game.py:541-576) inlined, up to
-// the point where next_turn would call end_hand (turn == 4).  The reference walks seat by seat from
-// active_player until it finds an ACTIVE seat, and calls next_turn when it arrives back at the seat
-// that just acted (`current_player`) without finding one: that is "first ACTIVE seat of the cyclic
-// interval [active_player .. current_player], else next_turn".
+// One Game.next_turn (game.py:541-576) up to the point where it would call end_hand (turn == 4);
+// returns false when the step must stop here (loop cap, or end_hand is due).
+template <int P, class V>
+PKB_D bool next_turn_once(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
+{
+    m.act = c.cur;
+    if (c.nt >= NEXT_TURN_CAP) {  // the reference has no termination guarantee here
+        c.poisoned = 1;
+        return false;
+    }
+    ++c.nt;
+    commit<P>(v, s);  // :554-558
+    m.turn += 1;      // :561
+    if (m.turn == 4) {  // :563-565 -> end_hand, then `return game_over, True, True`
+        c.pc = PC_END_HAND;
+        c.cont = 1;
+        return false;
+    }
+    if (popc32(x.called) > 1) {  // :567-572
+        x.active |= x.called;
+        x.called = 0;
+    }
+    m.act = first_playing<P>(x, m.dealer + 1);  // :575
+    c.done = (int)F_ROUND_OVER;                 // :576
+    return true;
+}
+
+// The `while` of Game.next_player (game.py:607-611) with next_turn inlined.  The reference walks seat
+// by seat from active_player until it finds an ACTIVE seat, and calls next_turn when it arrives back
+// at the seat that just acted (`current_player`) without finding one: that is "first ACTIVE seat of
+// the cyclic interval [active_player .. current_player], else next_turn".
+// After ONE next_turn nothing that the search looks at can change any more: pending is zero (further
+// commits add 0.0), CALLED seats were merged into ACTIVE (or there is at most one, which never
+// merges), and the search restarts from the same seat.  So if the search fails again, every further
+// next_turn fails the same way until turn == 4 ("streets skipped"): the
+// remaining streets are run out in closed form.
 template <int P, class V>
 PKB_D void seat_scan(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
 {
     c.pc = PC_DONE;
-    for (;;) {
-        const uint32_t cand = x.active & cyclic_interval<P>(m.act, c.cur);
-        if (cand) {
-            m.act = first_from(cand, m.act);
-            return;
+    uint32_t cand = x.active & cyclic_interval<P>(m.act, c.cur);
+    if (!cand) {
+        if (!next_turn_once<P>(v, s, x, m, c)) return;
+        cand = x.active & cyclic_interval<P>(m.act, c.cur);
+        if (!cand) {
+            const int more = 4 - m.turn;  // next_turn calls until turn == 4
+            if (c.nt + more <= NEXT_TURN_CAP) {
+                c.nt += more;
+                m.turn = 4;
+                m.act = c.cur;
+                c.pc = PC_END_HAND;
+                c.cont = 1;
+                return;
+            }
+            do {  // the loop cap falls inside the run-out: step through it call by call
+                if (!next_turn_once<P>(v, s, x, m, c)) return;
+                cand = x.active & cyclic_interval<P>(m.act, c.cur);
+            } while (!cand);
         }
-        m.act = c.cur;
-        if (c.nt >= NEXT_TURN_CAP) {  // the reference has no termination guarantee here
-            c.poisoned = 1;
-            return;
-        }
-        ++c.nt;
-        commit<P>(v, s);  // :554-558
-        m.turn += 1;      // :561
-        if (m.turn == 4) {  // :563-565 -> end_hand, then `return game_over, True, True`
-            c.pc = PC_END_HAND;
-            c.cont = 1;
-            return;
-        }
-        if (popc32(x.called) > 1) {  // :567-572
-            x.active |= x.called;
-            x.called = 0;
-        }
-        m.act = first_playing<P>(x, m.dealer + 1);  // :575
-        c.done = (int)F_ROUND_OVER;                 // :576
     }
+    m.act = first_from(cand, m.act);
 }
 
-// Game.step up to the first end_hand (game.py:648-699 and 597-605)
+// Game.step up to the first end_hand (game.py:648-699 and 597-605).  `vmask`, `hb`, `credit`: the
+// actor's valid mask and the high bet / stack it was computed from.
 template <int P, class V>
-PKB_D void step_begin(V& v, size_t s, Seats& x, Meta& m, Ctl& c, int action, uint32_t vmask, const GameConst& gc)
+PKB_D void step_begin(V& v, size_t s, Seats& x, Meta& m, Ctl& c, int action, uint32_t vmask, double hb, double credit,
+                      const GameConst& gc)
 {
     c = Ctl{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
     if (action < 0 || action >= NUM_MOVES || !(vmask >> action & 1u)) {  // :648-651, before any mutation
         c.invalid = 1;
         return;
     }
-    apply_action<P>(v, s, x, m.act, action, gc);
+    apply_action<P>(v, s, x, m.act, action, hb, credit, gc);
     if (popc32(x.active | x.called | x.allin) > 1) {  // :598-605
         c.cur = m.act;
         m.act = m.act + 1 == P ? 0 : m.act + 1;
@@ -368,7 +391,9 @@ template <int P, class V>
 PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c)
 {
     const size_t ld = v.ld();
-    commit<P>(v, s);  // :457-461; pending (= payoffs from here on) is now 0.0, :468
+    // :457-461; pending (= payoffs from here on) is 0.0 afterwards, :468.  When end_hand is entered from
+    // next_turn (c.cont) that call has just committed: pending and the minimum raise are already zero.
+    if (!c.cont) commit<P>(v, s);
     const uint32_t contenders = x.active | x.called | x.allin;  // :471 not BROKEN, not FOLDED
     const int n = popc32(contenders);
     c.npw = n;

@@ -1,12 +1,12 @@
 // pkb_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/pokerl_b200.h.
 //
 // Kernels
-//   step_kernel      K1+K2(+K5)  Game.step on a tile of envs staged in shared memory; end_hand and
-//                                the ranked showdown run on block-compacted slot lists
+//   step_tile_kernel K1+K2(+K5,K6) Game.step on tiles of envs held in shared memory: TMA bulk loads of the
+//                                SoA plane rows, three phases (every env / end_hand list / showdown
+//                                list) on block-compacted slot lists, TMA bulk stores
 //   reset_kernel     K3          Game.reset / setup_hand (dealing is a pure Philox function)
 //   eval_*_kernel    K4          eval_hand on card lists / id masks / all C(52,k) hands
 //   sample_kernel    K5          RandomAgent over the valid mask
-//   (K6, the statistics reduction, is fused into step_kernel's epilogue)
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
@@ -28,12 +28,8 @@ struct DevState {
     double *cr, *bt, *pd, *mr, *payoffs;
     uint8_t* st;
     uint32_t *meta, *hand, *episode;
-    unsigned long long* stats;  // [6] counters
+    unsigned long long* stats;  // [STAT_COUNT] counters
     double* payoff_sum;         // [MAX_PLAYERS]
-    uint32_t* ctl;              // [stride] automaton control word of envs parked between the step kernels
-    uint32_t* list_e;           // [stride] envs whose hand ended in this step (work list of kernel B)
-    uint32_t* list_s;           // [stride] envs that need a ranked showdown (work list of kernel C)
-    uint32_t* counters;         // [4] list lengths: {e, s} x step parity
     uint64_t n, stride;
 };
 
@@ -49,27 +45,21 @@ struct StepArgs {
     uint32_t step_idx;
     uint32_t use_weights;
     uint32_t weights[NUM_MOVES];
-    uint32_t parity;  // which pair of list counters this step uses; the other pair is zeroed for the next step
-    // the slice of the handle's envs this launch works on (slices run concurrently on internal streams)
-    uint32_t env_lo, env_cnt;  // first local env, number of env slots (a multiple of the block size)
-    uint32_t* list_e;          // [env_cnt] work list of kernel B
-    uint32_t* list_s;          // [env_cnt] work list of kernel C
-    uint32_t* counters;        // [4] list lengths: {e, s} x step parity
+    uint32_t num_tiles;
 };
 
-constexpr int TILE = 256;         // env-count granularity of the HBM planes (stride is a multiple of it)
-constexpr int STEP_THREADS = 128; // block size of the three step kernels (one env per thread)
-constexpr int MAX_SLICES = 16;    // env slices of one handle that may be stepped concurrently
-#ifndef PKB_BC_MIN_BLOCKS
-#define PKB_BC_MIN_BLOCKS 4
+constexpr int STRIDE_ALIGN = 1024;  // env-count granularity of the HBM planes: a multiple of every tile size
+constexpr int STEP_THREADS = 256;   // block size of the step kernel
+#ifndef PKB_STEP_MIN_BLOCKS
+#define PKB_STEP_MIN_BLOCKS 3
 #endif
-constexpr int BC_MIN_BLOCKS = PKB_BC_MIN_BLOCKS;  // resident blocks/SM kernels B and C are compiled for (register cap)
 
-// bytes of shared memory per thread-slot: f64 planes (3P+1), meta/hand u32, P state bytes
+// envs per tile: the tile (78 B per heads-up env, 278 B per ten-player env) stays well below 1/3 of
+// the 227 KB of shared memory so that three blocks are resident per SM
 template <int P>
-__host__ __device__ constexpr size_t slot_bytes()
+__host__ __device__ constexpr int tile_envs()
 {
-    return (size_t)(3 * P + 1) * 8 + 2 * 4 + P;
+    return P <= 4 ? 512 : 256;
 }
 
 PKB_D View<0> global_view(const DevState& d)
@@ -77,114 +67,158 @@ PKB_D View<0> global_view(const DevState& d)
     return View<0>{d.cr, d.bt, d.pd, d.mr, d.st, d.meta, d.hand, (size_t)d.stride};
 }
 
-// Per-thread staging of one env in shared memory ([field][thread] layout: bank-conflict free, and
-// seats can be indexed dynamically without spilling register arrays to local memory)
+// ---- shared-memory tile: [field][slot] rows in the same order and element types as the HBM
+// planes, so each row is ONE contiguous bulk copy in either direction -------------------------
 template <int P>
-PKB_D View<STEP_THREADS> carve_view(unsigned char* smem)
+struct Tile {
+    static constexpr int T = tile_envs<P>();
+    static constexpr int ROWS = 4 * P + 3;  // 3P f64 seat rows, mr, meta, hand, P state rows
+    static constexpr size_t OFF_BAR = 0;    // mbarrier (8 B) + list counters (2 x u32)
+    static constexpr size_t OFF_CR = 16;
+    static constexpr size_t OFF_BT = OFF_CR + (size_t)P * T * 8;
+    static constexpr size_t OFF_PD = OFF_BT + (size_t)P * T * 8;
+    static constexpr size_t OFF_MR = OFF_PD + (size_t)P * T * 8;
+    static constexpr size_t OFF_META = OFF_MR + (size_t)T * 8;
+    static constexpr size_t OFF_HAND = OFF_META + (size_t)T * 4;
+    static constexpr size_t OFF_ST = OFF_HAND + (size_t)T * 4;
+    static constexpr size_t OFF_CTL = OFF_ST + (size_t)P * T;      // u32 control word of parked slots
+    static constexpr size_t OFF_LIST_E = OFF_CTL + (size_t)T * 4;  // u16 slots whose hand ended
+    static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 2;  // u16 slots that need a ranked showdown
+    static constexpr size_t BYTES = OFF_LIST_S + (size_t)T * 2;
+    static constexpr uint32_t TX_BYTES = (uint32_t)((3 * P + 1) * T * 8 + 2 * T * 4 + P * T);
+};
+
+PKB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PKB_D void mbar_init(uint32_t bar, uint32_t count)
 {
-    View<STEP_THREADS> v;
-    double* f64 = reinterpret_cast<double*>(smem);
-    v.cr = f64;
-    v.bt = f64 + P * STEP_THREADS;
-    v.pd = f64 + 2 * P * STEP_THREADS;
-    v.mr = f64 + 3 * P * STEP_THREADS;
-    uint32_t* u32 = reinterpret_cast<uint32_t*>(f64 + (3 * P + 1) * STEP_THREADS);
-    v.meta = u32;
-    v.hand = u32 + STEP_THREADS;
-    v.st = reinterpret_cast<uint8_t*>(u32 + 2 * STEP_THREADS);
-    v.ld_rt = STEP_THREADS;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PKB_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+PKB_D void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copies (SASS: UBLKCP); sizes and addresses are multiples of 16 bytes
+PKB_D void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+PKB_D void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+PKB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PKB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+PKB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// row r of the tile: where it lives in HBM (for the tile that starts at env `base`) and in shared memory
+template <int P>
+PKB_D void tile_row(const DevState& d, size_t base, int r, char*& gptr, uint32_t& soff, uint32_t& bytes)
+{
+    using L = Tile<P>;
+    constexpr int T = L::T;
+    if (r < 3 * P) {
+        const int plane = r / P, seat = r - plane * P;
+        double* g = plane == 0 ? d.cr : plane == 1 ? d.bt : d.pd;
+        gptr = reinterpret_cast<char*>(g + (size_t)seat * d.stride + base);
+        soff = (uint32_t)(L::OFF_CR + (size_t)r * T * 8);
+        bytes = T * 8;
+    } else if (r == 3 * P) {
+        gptr = reinterpret_cast<char*>(d.mr + base);
+        soff = (uint32_t)L::OFF_MR;
+        bytes = T * 8;
+    } else if (r == 3 * P + 1) {
+        gptr = reinterpret_cast<char*>(d.meta + base);
+        soff = (uint32_t)L::OFF_META;
+        bytes = T * 4;
+    } else if (r == 3 * P + 2) {
+        gptr = reinterpret_cast<char*>(d.hand + base);
+        soff = (uint32_t)L::OFF_HAND;
+        bytes = T * 4;
+    } else {
+        const int seat = r - (3 * P + 3);
+        gptr = reinterpret_cast<char*>(d.st + (size_t)seat * d.stride + base);
+        soff = (uint32_t)(L::OFF_ST + (size_t)seat * T);
+        bytes = T;
+    }
+}
+
+template <int P>
+PKB_D View<Tile<P>::T> tile_view(unsigned char* smem)
+{
+    using L = Tile<P>;
+    View<L::T> v;
+    v.cr = reinterpret_cast<double*>(smem + L::OFF_CR);
+    v.bt = reinterpret_cast<double*>(smem + L::OFF_BT);
+    v.pd = reinterpret_cast<double*>(smem + L::OFF_PD);
+    v.mr = reinterpret_cast<double*>(smem + L::OFF_MR);
+    v.meta = reinterpret_cast<uint32_t*>(smem + L::OFF_META);
+    v.hand = reinterpret_cast<uint32_t*>(smem + L::OFF_HAND);
+    v.st = smem + L::OFF_ST;
+    v.ld_rt = L::T;
     return v;
 }
 
-// HBM planes -> the thread's staging slot; the seat states come back as masks (registers)
+// warp-aggregated append of a slot to a block-local work list (shared-memory counter)
+PKB_D void list_append(uint16_t* list, uint32_t* counter, bool mine, uint32_t slot)
+{
+    const unsigned vote = __ballot_sync(__activemask(), mine);
+    if (!mine) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)vote) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(vote));
+    base = __shfl_sync(vote, base, leader);
+    list[base + (uint32_t)__popc(vote & ((1u << lane) - 1u))] = (uint16_t)slot;
+}
+
+// per-thread statistics of one launch, reduced once per block
 template <int P>
-PKB_D Seats load_env(View<STEP_THREADS>& v, int t, const DevState& d, size_t env)
-{
-    const View<0> g = global_view(d);
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        v.cr[p * STEP_THREADS + t] = d.cr[p * d.stride + env];
-        v.bt[p * STEP_THREADS + t] = d.bt[p * d.stride + env];
-        v.pd[p * STEP_THREADS + t] = d.pd[p * d.stride + env];
-    }
-    v.mr[t] = d.mr[env];
-    v.meta[t] = d.meta[env];
-    v.hand[t] = d.hand[env];
-    return load_seats<P>(g, env);
-}
-
-template <int P>
-PKB_D void store_env(const View<STEP_THREADS>& v, int t, const Seats& x, const DevState& d, size_t env)
-{
-    View<0> g = global_view(d);
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        d.cr[p * d.stride + env] = v.cr[p * STEP_THREADS + t];
-        d.bt[p * d.stride + env] = v.bt[p * STEP_THREADS + t];
-        d.pd[p * d.stride + env] = v.pd[p * STEP_THREADS + t];
-    }
-    d.mr[env] = v.mr[t];
-    d.meta[env] = v.meta[t];
-    d.hand[env] = v.hand[t];
-    store_seats<P>(g, env, x);
-}
-
-// block-aggregated append of env ids to a work list: one global atomic per block, entries in
-// thread order.  Must be reached by every thread of the block.
-PKB_D void list_append(uint32_t* list, uint32_t* counter, bool mine, uint32_t env)
-{
-    __shared__ uint32_t s_warp[STEP_THREADS / 32], s_base;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned vote = __ballot_sync(0xffffffffu, mine);
-    if (lane == 0) s_warp[wid] = (uint32_t)__popc(vote);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int i = 0; i < STEP_THREADS / 32; ++i) total += s_warp[i];
-        s_base = total ? atomicAdd(counter, total) : 0u;
-    }
-    __syncthreads();
-    if (mine) {
-        uint32_t at = s_base + (uint32_t)__popc(vote & ((1u << lane) - 1u));
-        for (int i = 0; i < wid; ++i) at += s_warp[i];
-        list[at] = env;
-    }
-    __syncthreads();  // s_warp / s_base are reused by the next call
-}
-
-// warp-aggregated event counter -> one global atomic per warp that saw the event
-PKB_D void count_events(unsigned long long* counter, bool event)
-{
-    const unsigned vote = __ballot_sync(0xffffffffu, event);
-    if (vote && (threadIdx.x & 31) == 0) atomicAdd(counter, (unsigned long long)__popc(vote));
-}
+struct Tally {
+    double pay[P];
+    uint32_t hands, shows, games, poisoned, invalid, live;
+};
 
 // Step outputs of one finished env: flag bits and the valid mask of the new active player
-template <int P>
-PKB_D uint32_t write_outputs(const View<STEP_THREADS>& v, int t, const Ctl& c, const StepArgs& a, size_t env)
+template <int P, class V>
+PKB_D uint32_t write_outputs(const V& v, int s, const Ctl& c, const StepArgs& a, size_t env)
 {
     const uint32_t f = (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
     if (a.flags) a.flags[env] = (uint8_t)f;
-    if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(v, t, unpack_meta(v.meta[t]).act);
+    if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(v, s, unpack_meta(v.meta[s]).act);
     return f;
 }
 
 // What follows Game.end_hand once the payoffs are in the pending plane (game.py:530-539 and the
 // caller's use of the return value), then Game.reset() if the game ended and auto-reset is on.
 // Leaves c.pc == PC_END_HAND when ANOTHER hand ends inside the same step (rare: all-in blinds).
-template <int P>
-PKB_D void finish_hand(View<STEP_THREADS>& v, int t, Seats& x, Meta& m, Ctl& c, const StepArgs& a, size_t env,
-                       double (&paysum)[P])
+template <int P, class V>
+PKB_D void finish_hand(V& v, int s, Seats& x, Meta& m, Ctl& c, const StepArgs& a, size_t env, Tally<P>& tl)
 {
     const DevState& d = a.d;
     double pay[P];
-    end_hand_finish<P>(v, t, x, m, c, d.payoffs, d.stride, env, pay, a.gc);
+    end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc);
 #pragma unroll
-    for (int p = 0; p < P; ++p) paysum[p] += pay[p];
+    for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
     if (c.pc == PC_DONE && (c.done & (int)F_GAME_OVER) && !c.poisoned && a.gc.auto_reset) {
         d.episode[env] += 1;  // Game.reset() right after the step that ended the game (game.py:397-412)
-        reset_env<P>(v, t, x, m, a.gc);
+        reset_env<P>(v, s, x, m, a.gc);
     }
 }
 
@@ -199,188 +233,204 @@ PKB_D void assert_exit(const Seats& x, Ctl& c, const StepArgs& a, size_t env)
     c.pc = PC_DONE;
 }
 
-// block reduction of the per-thread payoff sums and counters into the handle's statistics
+// block reduction of the per-thread tallies into the handle's statistics
 template <int P>
-PKB_D void reduce_stats(const DevState& d, const double (&paysum)[P], uint32_t hands, uint32_t shows, uint32_t games,
-                        uint32_t poisoned)
+PKB_D void reduce_stats(const DevState& d, const Tally<P>& tl)
 {
     __shared__ double s_pay[MAX_PLAYERS];
-    __shared__ uint32_t s_cnt[4];
+    __shared__ uint32_t s_cnt[6];
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < MAX_PLAYERS) s_pay[tid] = 0.0;
-    if (tid < 4) s_cnt[tid] = 0;
+    if (tid < 6) s_cnt[tid] = 0;
     __syncthreads();
-    const uint32_t cnt[4] = {hands, shows, games, poisoned};
+    const uint32_t cnt[6] = {tl.live, tl.hands, tl.shows, tl.games, tl.invalid, tl.poisoned};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
         const uint32_t w = __reduce_add_sync(0xffffffffu, cnt[i]);
         if (lane == 0 && w) atomicAdd(&s_cnt[i], w);
     }
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        double x = paysum[p];
+        double x = tl.pay[p];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x != 0.0) atomicAdd(&s_pay[p], x);
     }
     __syncthreads();
-    if (tid == 0 && s_cnt[0]) atomicAdd(&d.stats[STAT_HANDS], (unsigned long long)s_cnt[0]);
-    if (tid == 1 && s_cnt[1]) atomicAdd(&d.stats[STAT_SHOWDOWNS], (unsigned long long)s_cnt[1]);
-    if (tid == 2 && s_cnt[2]) atomicAdd(&d.stats[STAT_GAMES], (unsigned long long)s_cnt[2]);
-    if (tid == 3 && s_cnt[3]) atomicAdd(&d.stats[STAT_POISONED], (unsigned long long)s_cnt[3]);
+    // STAT_STEPS counts every live env of the launch; pkb_stats subtracts the invalid ones
+    if (tid < 6 && s_cnt[tid]) atomicAdd(&d.stats[tid], (unsigned long long)s_cnt[tid]);
     if (tid >= 32 && tid < 32 + P && s_pay[tid - 32] != 0.0) atomicAdd(&d.payoff_sum[tid - 32], s_pay[tid - 32]);
 }
 
 // --------------------------------------------------------------------------------------------
-// Game.step (game.py:621-700) as a three-kernel pipeline over the SoA planes.  The branches of a
-// step differ by 10-100x in cost (a bet; a hand that ends; a ranked showdown), so instead of letting
-// warps diverge, each kernel runs ONE kind of work at full warp width and hands the rest on
-// through a compacted env list in HBM:
-//   A  every env:          validate/sample the action, bet, seat scan, next_turn commits  -> list E
-//   B  envs in list E:     end_hand: commit, last-stand pots, deal the next hand, resume    -> list S
-//   C  envs in list S:     ranked showdown (deal replay, 7-card ranks, side pots), then as B
-// Each kernel is small (instruction-cache resident) and streams state through shared memory.
+// Game.step (game.py:621-700) on every env.  A persistent block walks tiles of T envs; a tile's
+// plane rows are pulled into shared memory by TMA bulk copies, stepped in place, and pushed back,
+// so each env's state crosses HBM exactly once in each direction per step.
+// The branches of a step differ by 10-100x in cost (a bet; a hand that ends; a ranked showdown),
+// so instead of letting warps diverge the block runs three phases over the tile, handing the
+// expensive cases on through compacted slot lists so that each phase runs at full warp width:
+//   A  every slot:          validate/sample the action, bet, seat scan, next_turn commits  -> list E
+//   B  slots in list E:     end_hand: commit, last-stand pots, set up the next hand, resume -> list S
+//   C  slots in list S:     ranked showdown (deal replay, 7-card ranks, side pots), then as B
 // --------------------------------------------------------------------------------------------
-
-// K1: one thread per env, fully coalesced loads/stores
 template <int P, bool SAMPLE>
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel_a(const __grid_constant__ StepArgs a)
+__global__ void __launch_bounds__(STEP_THREADS, PKB_STEP_MIN_BLOCKS) step_tile_kernel(const __grid_constant__ StepArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    View<STEP_THREADS> v = carve_view<P>(smem_raw);
+    using L = Tile<P>;
+    constexpr int T = L::T;
+    extern __shared__ __align__(128) unsigned char smem[];
+    View<T> v = tile_view<P>(smem);
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + L::OFF_CTL);
+    uint16_t* list_e = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST_E);
+    uint16_t* list_s = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST_S);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8);
+    const uint32_t bar = smem_u32(smem + L::OFF_BAR), smem_base = smem_u32(smem);
     const DevState& d = a.d;
-    const int t = threadIdx.x;
-    const size_t env = (size_t)a.env_lo + (size_t)blockIdx.x * STEP_THREADS + t;
-    const bool live = env < d.n;
-    if (blockIdx.x == 0 && t < 2) a.counters[2 * (a.parity ^ 1u) + t] = 0;  // next step's list lengths
+    const int tid = threadIdx.x;
 
-    Seats x = load_env<P>(v, t, d, env);  // stride is a multiple of the block size: always in bounds
-    Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
-    if (live) {
-        Meta m = unpack_meta(v.meta[t]);
-        const uint32_t vm = valid_mask<P>(v, t, m.act);
-        int action;
-        if (SAMPLE) {
-            action = sample_action(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx, vm,
-                                   a.use_weights ? a.weights : nullptr);
-            if (a.actions_out) a.actions_out[env] = action;
-        } else
-            action = a.actions[env];
-        step_begin<P>(v, t, x, m, c, action, vm, a.gc);
-        v.meta[t] = pack_meta(m);
-    }
-    const bool parked = live && c.pc == PC_END_HAND;
-    if (live) {
-        if (!c.invalid) store_env<P>(v, t, x, d, env);  // an invalid action changes nothing (game.py:649-651)
-        if (parked) d.ctl[env] = pack_ctl(c);
-        else write_outputs<P>(v, t, c, a, env);
-    }
-    list_append(a.list_e, &a.counters[2 * a.parity], parked, (uint32_t)env);
-    if (a.gc.track_stats) {
-        count_events(&d.stats[STAT_INVALID], live && c.invalid);
-        count_events(&d.stats[STAT_POISONED], live && c.poisoned);
-        if (blockIdx.x == 0 && t == 0) {  // live envs of this slice; pkb_stats subtracts the invalid ones
-            const size_t hi = (size_t)a.env_lo + a.env_cnt;
-            atomicAdd(&d.stats[STAT_STEPS], (unsigned long long)((hi < d.n ? hi : d.n) - a.env_lo));
-        }
-    }
-}
+    if (tid == 0) mbar_init(bar, L::ROWS);
+    __syncthreads();
 
-// K2a: end_hand for the envs in list E
-template <int P>
-__global__ void __launch_bounds__(STEP_THREADS, BC_MIN_BLOCKS) step_kernel_b(const __grid_constant__ StepArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    View<STEP_THREADS> v = carve_view<P>(smem_raw);
-    const DevState& d = a.d;
-    const int t = threadIdx.x;
-    const uint32_t n_items = a.counters[2 * a.parity];
-    uint32_t games = 0, poisoned = 0;
-    double paysum[P];
+    Tally<P> tl;
 #pragma unroll
-    for (int p = 0; p < P; ++p) paysum[p] = 0.0;
-    const uint32_t rounded = (n_items + STEP_THREADS - 1) / STEP_THREADS * STEP_THREADS;
-    for (uint32_t i = blockIdx.x * STEP_THREADS + t; i < rounded; i += gridDim.x * STEP_THREADS) {
-        const bool active = i < n_items;
-        bool to_c = false;
-        size_t env = 0;
-        if (active) {
-            env = a.list_e[i];
-            Seats x = load_env<P>(v, t, d, env);
-            Ctl c = unpack_ctl(d.ctl[env]);
-            Meta m = unpack_meta(v.meta[t]);
-            if (end_hand_begin<P>(v, t, x, c)) {
+    for (int p = 0; p < P; ++p) tl.pay[p] = 0.0;
+    tl.hands = tl.shows = tl.games = tl.poisoned = tl.invalid = tl.live = 0;
+    uint32_t parity = 0;
+
+    for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const size_t base = (size_t)tile * T;
+        // ---- load: thread r owns row r in both directions
+        if (tid < L::ROWS) {
+            char* g;
+            uint32_t soff, bytes;
+            tile_row<P>(d, base, tid, g, soff, bytes);
+            bulk_wait_read();  // the previous tile's store of this row has left shared memory
+            if (tid == 0) cnt[0] = cnt[1] = 0;
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_load(smem_base + soff, g, bytes, bar);
+        }
+        // the random words do not depend on the state: draw them while the tile is in flight
+        uint32_t word[T / STEP_THREADS];
+        if (SAMPLE) {
+#pragma unroll
+            for (int e = 0; e < T / STEP_THREADS; ++e)
+                word[e] = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)(base + e * STEP_THREADS + tid), a.step_idx);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        // ---- phase A: every slot
+#pragma unroll
+        for (int e = 0; e < T / STEP_THREADS; ++e) {
+            const int s = e * STEP_THREADS + tid;
+            const size_t env = base + s;
+            const bool live = env < d.n;
+            Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
+            if (live) {
+                Seats x = load_seats<P>(v, s);
+                Meta m = unpack_meta(v.meta[s]);
+                const double hb = high_bet<P>(v, s), credit = v.cr[m.act * T + s];
+                const uint32_t vm = valid_mask_from(hb, credit, v.mr[s]);
+                int action;
+                if (SAMPLE) {
+                    action = a.use_weights ? pick_weighted(word[e], vm, a.weights) : pick_uniform(word[e], vm);
+                    if (a.actions_out) a.actions_out[env] = action;
+                } else
+                    action = a.actions[env];
+                step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
+                if (!c.invalid) {  // an invalid action changes nothing (game.py:649-651)
+                    store_seats<P>(v, s, x);
+                    v.meta[s] = pack_meta(m);
+                }
+                ++tl.live;
+                tl.invalid += (uint32_t)c.invalid;
+                if (c.pc == PC_END_HAND) ctl[s] = pack_ctl(c);
+                else tl.poisoned += (uint32_t)c.poisoned, write_outputs<P>(v, s, c, a, env);
+            }
+            list_append(list_e, &cnt[0], live && c.pc == PC_END_HAND, (uint32_t)s);
+        }
+        __syncthreads();
+
+        // ---- phase B: end_hand for the slots in list E
+        const uint32_t n_e = cnt[0];
+        for (uint32_t i = tid; i < n_e; i += STEP_THREADS) {
+            const int s = list_e[i];
+            const size_t env = base + s;
+            Seats x = load_seats<P>(v, s);
+            Ctl c = unpack_ctl(ctl[s]);
+            Meta m = unpack_meta(v.meta[s]);
+            bool to_c = false;
+            ++tl.hands;
+            if (end_hand_begin<P>(v, s, x, c)) {
                 c.pc = PC_SHOWDOWN;
                 to_c = true;
             } else if (c.poisoned) {
                 assert_exit<P>(x, c, a, env);
             } else {
-                finish_hand<P>(v, t, x, m, c, a, env, paysum);
-                to_c = c.pc == PC_END_HAND;  // another hand ends inside this step: kernel C runs it
+                finish_hand<P>(v, s, x, m, c, a, env, tl);
+                to_c = c.pc == PC_END_HAND;  // another hand ends inside this step: phase C runs it
             }
-            v.meta[t] = pack_meta(m);
-            store_env<P>(v, t, x, d, env);
-            if (to_c) d.ctl[env] = pack_ctl(c);
+            v.meta[s] = pack_meta(m);
+            store_seats<P>(v, s, x);
+            if (to_c) ctl[s] = pack_ctl(c);
             else {
-                const uint32_t f = write_outputs<P>(v, t, c, a, env);
-                games += (f & F_GAME_OVER) ? 1u : 0u;
-                poisoned += c.poisoned ? 1u : 0u;
+                const uint32_t f = write_outputs<P>(v, s, c, a, env);
+                tl.games += (f & F_GAME_OVER) ? 1u : 0u;
+                tl.poisoned += (uint32_t)c.poisoned;
             }
+            list_append(list_s, &cnt[1], to_c, (uint32_t)s);
         }
-        list_append(a.list_s, &a.counters[2 * a.parity + 1], to_c, (uint32_t)env);
-    }
-    if (a.gc.track_stats) {
-        const uint32_t hands = (blockIdx.x == 0 && t == 0) ? n_items : 0u;
-        reduce_stats<P>(d, paysum, hands, 0u, games, poisoned);
-    }
-}
+        __syncthreads();
 
-// K2b: ranked showdowns (and the rare further hands of a step) for the envs in list S
-template <int P>
-__global__ void __launch_bounds__(STEP_THREADS, BC_MIN_BLOCKS) step_kernel_c(const __grid_constant__ StepArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    View<STEP_THREADS> v = carve_view<P>(smem_raw);
-    const DevState& d = a.d;
-    const int t = threadIdx.x;
-    const uint32_t n_items = a.counters[2 * a.parity + 1];
-    uint32_t hands = 0, shows = 0, games = 0, poisoned = 0;
-    double paysum[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) paysum[p] = 0.0;
-    for (uint32_t i = blockIdx.x * STEP_THREADS + t; i < n_items; i += gridDim.x * STEP_THREADS) {
-        const size_t env = a.list_s[i];
-        Seats x = load_env<P>(v, t, d, env);
-        Ctl c = unpack_ctl(d.ctl[env]);
-        Meta m = unpack_meta(v.meta[t]);
-        const uint32_t episode = d.episode[env];
-        bool asserted = false;
-        while (c.pc != PC_DONE) {
-            bool ranked = c.pc == PC_SHOWDOWN;
-            if (!ranked) {  // PC_END_HAND: a further hand of this step, from its beginning
-                ++hands;
-                ranked = end_hand_begin<P>(v, t, x, c);
-                if (!ranked && c.poisoned) {
-                    asserted = true;
-                    break;
+        // ---- phase C: ranked showdowns (and the rare further hands of a step) for the slots in list S
+        const uint32_t n_s = cnt[1];
+        for (uint32_t i = tid; i < n_s; i += STEP_THREADS) {
+            const int s = list_s[i];
+            const size_t env = base + s;
+            Seats x = load_seats<P>(v, s);
+            Ctl c = unpack_ctl(ctl[s]);
+            Meta m = unpack_meta(v.meta[s]);
+            const uint32_t episode = d.episode[env];
+            bool asserted = false;
+            while (c.pc != PC_DONE) {
+                bool ranked = c.pc == PC_SHOWDOWN;
+                if (!ranked) {  // PC_END_HAND: a further hand of this step, from its beginning
+                    ++tl.hands;
+                    ranked = end_hand_begin<P>(v, s, x, c);
+                    if (!ranked && c.poisoned) {
+                        asserted = true;
+                        break;
+                    }
                 }
+                if (ranked) {
+                    ++tl.shows;
+                    showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode,
+                                [](uint64_t mask) { return eval_mask52(mask); });
+                }
+                c.pc = PC_DONE;
+                finish_hand<P>(v, s, x, m, c, a, env, tl);
             }
-            if (ranked) {
-                ++shows;
-                showdown<P>(v, t, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode,
-                            [](uint64_t mask) { return eval_mask52(mask); });
-            }
-            c.pc = PC_DONE;
-            finish_hand<P>(v, t, x, m, c, a, env, paysum);
+            if (asserted) assert_exit<P>(x, c, a, env);
+            v.meta[s] = pack_meta(m);
+            store_seats<P>(v, s, x);
+            const uint32_t f = write_outputs<P>(v, s, c, a, env);
+            tl.games += (f & F_GAME_OVER) ? 1u : 0u;
+            tl.poisoned += (uint32_t)c.poisoned;
         }
-        if (asserted) assert_exit<P>(x, c, a, env);
-        v.meta[t] = pack_meta(m);
-        store_env<P>(v, t, x, d, env);
-        const uint32_t f = write_outputs<P>(v, t, c, a, env);
-        games += (f & F_GAME_OVER) ? 1u : 0u;
-        poisoned += c.poisoned ? 1u : 0u;
+
+        // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
+        fence_async_smem();
+        __syncthreads();
+        if (tid < L::ROWS) {
+            char* g;
+            uint32_t soff, bytes;
+            tile_row<P>(d, base, tid, g, soff, bytes);
+            bulk_store(g, smem_base + soff, bytes);
+            bulk_commit();
+        }
     }
-    if (a.gc.track_stats) reduce_stats<P>(d, paysum, hands, shows, games, poisoned);
+    if (tid < L::ROWS) bulk_wait_all();
+    if (a.gc.track_stats) reduce_stats<P>(d, tl);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -594,21 +644,10 @@ struct pkb_env {
     void* arena;
     size_t arena_bytes;
     uint32_t* d_weights;
-    uint32_t parity;  // step parity: which pair of list counters the next step uses
-    // env slices stepped concurrently on internal streams (fork/join around the caller's stream)
-    int num_slices;
-    cudaStream_t streams[MAX_SLICES];
-    cudaEvent_t fork, join[MAX_SLICES];
+    int sm_count;
 };
 
 static thread_local std::string g_error;
-
-static int slices_from_env()
-{
-    const char* e = getenv("PKB_SLICES");
-    int n = e ? atoi(e) : 1;
-    return n < 1 ? 1 : (n > MAX_SLICES ? MAX_SLICES : n);
-}
 
 static int fail(const char* what, cudaError_t e = cudaSuccess)
 {
@@ -642,27 +681,25 @@ static int fail(const char* what, cudaError_t e = cudaSuccess)
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// One launch per step: a persistent grid of as many blocks as fit the device at once.
 template <int P, bool SAMPLE>
-static cudaError_t launch_step(const StepArgs& a, cudaStream_t s)
+static cudaError_t launch_step(const StepArgs& a, cudaStream_t s, int device, int sm_count)
 {
-    constexpr size_t smem = slot_bytes<P>() * STEP_THREADS;
-    static int sm_count[64] = {0};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (!sm_count[dev]) {
-        e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    constexpr size_t smem = Tile<P>::BYTES;
+    static int blocks_per_sm[64] = {0};
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (!blocks_per_sm[device]) {
+        cudaError_t e = cudaFuncSetAttribute(step_tile_kernel<P, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_tile_kernel<P, SAMPLE>, STEP_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (nb < 1) return cudaErrorLaunchOutOfResources;
+        blocks_per_sm[device] = nb;
     }
-    const unsigned blocks_a = a.env_cnt / STEP_THREADS;
-    // B and C read their item count on the device.  Their grids cover the usual share of envs whose
-    // hand ends (about 1/3) / is ranked (about 1/8) in one pass, so that all items are in flight at
-    // once; a grid stride handles anything beyond that, and surplus blocks exit at once.
-    const unsigned blocks_b = blocks_a / 2 + 1, blocks_c = blocks_a / 4 + 1;
-    step_kernel_a<P, SAMPLE><<<blocks_a, STEP_THREADS, smem, s>>>(a);
-    step_kernel_b<P><<<blocks_b, STEP_THREADS, smem, s>>>(a);
-    step_kernel_c<P><<<blocks_c, STEP_THREADS, smem, s>>>(a);
+    const unsigned resident = (unsigned)(blocks_per_sm[device] * sm_count);
+    const unsigned grid = a.num_tiles < resident ? a.num_tiles : resident;
+    step_tile_kernel<P, SAMPLE><<<grid, STEP_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -695,11 +732,11 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     pkb_env* h = new pkb_env();
     h->cfg = *cfg;
     const int P = cfg->num_players;
-    const uint64_t n = cfg->num_envs, stride = (n + TILE - 1) / TILE * TILE;
+    const uint64_t n = cfg->num_envs, stride = (n + STRIDE_ALIGN - 1) / STRIDE_ALIGN * STRIDE_ALIGN;
     // arena: f64 planes | u32 planes | u8 planes | stats
-    const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)6 * stride, n_u8 = (size_t)P * stride;
+    const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)3 * stride, n_u8 = (size_t)P * stride;
     const size_t off_u32 = n_f64 * 8, off_u8 = off_u32 + n_u32 * 4, off_stats = (off_u8 + n_u8 + 255) / 256 * 256;
-    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 4 * 4 * MAX_SLICES;
+    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) {
         delete h;
@@ -723,14 +760,10 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     d.meta = u;
     d.hand = u + stride;
     d.episode = u + 2 * stride;
-    d.ctl = u + 3 * stride;
-    d.list_e = u + 4 * stride;
-    d.list_s = u + 5 * stride;
     d.st = reinterpret_cast<uint8_t*>(base + off_u8);
     d.stats = reinterpret_cast<unsigned long long*>(base + off_stats);
     d.payoff_sum = reinterpret_cast<double*>(base + off_stats + STAT_COUNT * 8);
     h->d_weights = reinterpret_cast<uint32_t*>(base + off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8);
-    d.counters = h->d_weights + NUM_MOVES + 1;
     d.n = n;
     d.stride = stride;
 
@@ -744,20 +777,11 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     gc.dealer = cfg->dealer;
     gc.auto_reset = cfg->auto_reset;
     gc.track_stats = 1;
-    // slices: at least 64 blocks each, so small batches stay on the caller's stream
-    h->num_slices = slices_from_env();
-    while (h->num_slices > 1 && stride / h->num_slices < 64 * STEP_THREADS) --h->num_slices;
-    if (h->num_slices > 1) {
-        e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
-        for (int i = 0; i < h->num_slices && e == cudaSuccess; ++i) {
-            e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join[i], cudaEventDisableTiming);
-        }
-        if (e != cudaSuccess) {
-            cudaFree(h->arena);
-            delete h;
-            return fail("pkb_create: streams", e);
-        }
+    e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (e != cudaSuccess) {
+        cudaFree(h->arena);
+        delete h;
+        return fail("pkb_create: cudaDeviceGetAttribute", e);
     }
     *out = h;
     return 0;
@@ -767,14 +791,6 @@ int pkb_destroy(pkb_env* h)
 {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    if (h->num_slices > 1) {
-        for (int i = 0; i < h->num_slices; ++i) {
-            cudaStreamSynchronize(h->streams[i]);
-            cudaStreamDestroy(h->streams[i]);
-            cudaEventDestroy(h->join[i]);
-        }
-        cudaEventDestroy(h->fork);
-    }
     cudaFree(h->arena);
     delete h;
     return 0;
@@ -814,33 +830,14 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.valid = valid;
     a.step_idx = step_idx;
     a.use_weights = weights ? 1u : 0u;
-    a.parity = h->parity;
-    h->parity ^= 1u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
-    cudaStream_t caller = static_cast<cudaStream_t>(stream);
-    const int S = h->num_slices;
-    // slice boundaries on multiples of the block size
-    const uint64_t blocks = h->d.stride / STEP_THREADS, per = (blocks + S - 1) / S;
-    if (S > 1) PKB_CUDA(cudaEventRecord(h->fork, caller));
-    for (int i = 0; i < S; ++i) {
-        const uint64_t b0 = per * i, b1 = b0 + per < blocks ? b0 + per : blocks;
-        if (b0 >= b1) continue;
-        a.env_lo = (uint32_t)(b0 * STEP_THREADS);
-        a.env_cnt = (uint32_t)((b1 - b0) * STEP_THREADS);
-        a.list_e = h->d.list_e + a.env_lo;
-        a.list_s = h->d.list_s + a.env_lo;
-        a.counters = h->d.counters + 4 * i;
-        cudaStream_t s = S > 1 ? h->streams[i] : caller;
-        if (S > 1) PKB_CUDA(cudaStreamWaitEvent(s, h->fork, 0));
-        cudaError_t e = cudaSuccess;
-        PKB_DISPATCH_P(h->cfg.num_players,
-                       e = sample ? launch_step<P, true>(a, s) : launch_step<P, false>(a, s));
-        if (e != cudaSuccess) return fail("pkb_step: launch", e);
-        if (S > 1) {
-            PKB_CUDA(cudaEventRecord(h->join[i], s));
-            PKB_CUDA(cudaStreamWaitEvent(caller, h->join[i], 0));
-        }
-    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaSuccess;
+    PKB_DISPATCH_P(h->cfg.num_players,
+                   a.num_tiles = (uint32_t)((h->d.n + tile_envs<P>() - 1) / tile_envs<P>());
+                   e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count)
+                              : launch_step<P, false>(a, s, h->cfg.device, h->sm_count));
+    if (e != cudaSuccess) return fail("pkb_step: launch", e);
     return 0;
 }
 

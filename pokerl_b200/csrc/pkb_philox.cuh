@@ -77,25 +77,48 @@ struct Dealer {
     }
 };
 
-// weights == nullptr -> uniform
-PKB_HD int sample_action(uint64_t seed, uint32_t env_id, uint32_t step_idx, uint32_t valid_mask, const uint32_t* weights)
+// the 32-bit word that drives the action draw of (env, step): a pure function, independent of the state
+PKB_HD uint32_t sample_word(uint64_t seed, uint32_t env_id, uint32_t step_idx)
 {
-    const U4 r = philox4x32_10(U4{env_id, step_idx, 0u, 0x80000000u}, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32_10(U4{env_id, step_idx, 0u, 0x80000000u}, (uint32_t)seed, (uint32_t)(seed >> 32)).x;
+}
+
+// weighted choice over the valid mask: the first valid move whose cumulative weight exceeds t
+PKB_HD int pick_weighted(uint32_t word, uint32_t valid_mask, const uint32_t* weights)
+{
     uint32_t total = 0;
 #pragma unroll
     for (int a = 0; a < NUM_MOVES; ++a)
-        if (valid_mask >> a & 1u) total += weights ? weights[a] : 1u;
-    const uint32_t t = mulhi32(r.x, total);
+        if (valid_mask >> a & 1u) total += weights[a];
+    const uint32_t t = mulhi32(word, total);
     uint32_t acc = 0;
     int pick = MV_FOLD;
     bool found = false;
 #pragma unroll
     for (int a = 0; a < NUM_MOVES; ++a)
         if (valid_mask >> a & 1u) {
-            acc += weights ? weights[a] : 1u;
+            acc += weights[a];
             if (!found && acc > t) { pick = a; found = true; }
         }
     return pick;
+}
+
+// uniform weights: the t-th valid move, t = mulhi32(word, number of valid moves).  The position of
+// the t-th set bit equals the number of inclusive bit prefixes that hold at most t set bits.
+PKB_HD int pick_uniform(uint32_t word, uint32_t valid_mask)
+{
+    const uint32_t t = mulhi32(word, (uint32_t)popc32(valid_mask));
+    int pick = 0;
+#pragma unroll
+    for (int a = 0; a < NUM_MOVES - 1; ++a) pick += (uint32_t)popc32(valid_mask & ((2u << a) - 1u)) <= t ? 1 : 0;
+    return pick;
+}
+
+// weights == nullptr -> uniform
+PKB_HD int sample_action(uint64_t seed, uint32_t env_id, uint32_t step_idx, uint32_t valid_mask, const uint32_t* weights)
+{
+    const uint32_t word = sample_word(seed, env_id, step_idx);
+    return weights ? pick_weighted(word, valid_mask, weights) : pick_uniform(word, valid_mask);
 }
 
 }  // namespace pkb
