@@ -8,7 +8,7 @@
 Workload (BASELINE.json configs[2]): heads-up NLHE, 2^20 lockstep envs PER GPU, start_credits 100, blinds
 2/1, uniform random agents drawn on device from Philox(seed 0, global env id, step), auto-reset on
 game over.  One bench "step" = one Game.step on every env = one launch of the fused
-sample+step kernel.  Envs shard by contiguous global-id slices; there is no data-path collective
+sample+step kernel (pkb::step_tile_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective
 (weak scaling); one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
 
 Timing: W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket.  The
@@ -316,14 +316,14 @@ def run_ours(args, rank, local_rank, world):
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(N, world),
-        "roofline": {"bound": "hbm", "kernel": "pkb::step_kernel<2,true>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "pkb::step_tile_kernel<2,true>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("step_kernel_p2"),
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_step(P),
                      "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src},
         "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N,
                 "d2h_bytes_per_step": 2 * N, "steps": E,
                 "path": "GameBatch.step(actions from pinned host) -> pkb_step -> flags+valid to pinned host, sync per step"},
-        "gpu_launches": 3 * K,  # step_kernel_a/b/c per step
+        "gpu_launches": K,  # one persistent step_tile_kernel launch per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world * K / (resident_ms / 1e3), "unit": "env-steps/s",
                         "note": "same K steps back to back without the L2 flush (state stays in the 126 MB L2)"},

@@ -6,10 +6,12 @@
 #define PKB_HD __host__ __device__ __forceinline__
 #define PKB_HDM __host__ __device__ __forceinline__ /* member functions */
 #define PKB_D __device__ __forceinline__
+#define PKB_HD_CALL __host__ __device__ __noinline__ /* real calls: keeps the step kernel's code instruction-cache sized */
 #else
 #define PKB_HD static inline
 #define PKB_HDM inline
 #define PKB_D static inline
+#define PKB_HD_CALL static inline
 #endif
 
 namespace pkb {

@@ -43,7 +43,7 @@ PKB_HD uint32_t suit_ranks(uint64_t m, int suit)
     return (x >> 1) | ((x & 1u) << 12);
 }
 
-PKB_HD uint32_t eval_mask52(uint64_t m)
+PKB_HD_CALL uint32_t eval_mask52(uint64_t m)
 {
     if (m == 0) return PACKED_NONE;  // judger.py:30
     const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);

@@ -411,11 +411,10 @@ PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c)
     return true;
 }
 
-// Game.end_hand, ranked showdown (game.py:483-528).  `rank7(mask)` evaluates a 7-card id mask.
+// Game.end_hand, ranked showdown (game.py:483-528).
 // The working copy of bets is kept in registers; payoffs are written to the pending plane at the end.
-template <int P, class V, class Rank7>
-PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed, uint32_t env_id, uint32_t episode,
-                    Rank7 rank7)
+template <int P, class V>
+PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed, uint32_t env_id, uint32_t episode)
 {
     const size_t ld = v.ld();
     uint32_t rk[P];
@@ -429,7 +428,7 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const uint64_t hole = (1ull << d.next()) | (1ull << d.next());
-            rk[p] = (todo >> p & 1u) ? rank7(board | hole) : PACKED_NONE;
+            rk[p] = (todo >> p & 1u) ? eval_mask52(board | hole) : PACKED_NONE;
             b[p] = v.bt[p * ld + s];  // :485 working copy
             pay[p] = 0.0;
         }
@@ -496,8 +495,9 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
 
 // Game.end_hand, last part (game.py:530-539), then what the caller of end_hand does with its
 // return value (game.py:565 / 609-611 or game.py:619).  `pay_out` receives the hand's final payoffs.
+// With `auto_reset`, a finished game is reset right here (Game.reset, game.py:397-412).  Returns true if it reset.
 template <int P, class V>
-PKB_D void end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* payoffs_out, size_t out_ld, size_t out_idx,
+PKB_D bool end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* payoffs_out, size_t out_ld, size_t out_idx,
                            double (&pay_out)[P], const GameConst& gc)
 {
     const size_t ld = v.ld();
@@ -508,16 +508,34 @@ PKB_D void end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* pa
         payoffs_out[p * out_ld + out_idx] = pay;
         if (v.cr[p * ld + s] <= 0.0) set_state(x, p, ST_BROKEN);  // :536
     }
-    setup_hand<P>(v, s, x, m, gc);  // :539 -- runs even when the game is over
-    const int over = game_over<P>(x) ? (int)F_GAME_OVER : 0;
+    // :539 setup_hand runs even when the game is over -- and it can bring BROKEN seats with a negative
+    // stack back as ALL_IN, so game_over is read after it, as the callers do
+    // (:565, :619).  A second trip through the same code is Game.reset's setup_hand (:412).
+    bool over = false, reset_now = false;
+#pragma unroll 1
+    for (int trip = 0; trip < 2; ++trip) {
+        setup_hand<P>(v, s, x, m, gc);
+        if (trip == 1) break;
+        over = game_over<P>(x);
+        reset_now = over && gc.auto_reset && !c.poisoned;
+        if (!reset_now) break;
+        m.dealer = gc.dealer;  // Game.reset, :403-409
+        m.act = 0;
+        v.hand[s] = 0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) v.cr[p * ld + s] = gc.start_credits[p];
+        x = Seats{all_seats<P>(), 0, 0, 0};
+    }
+    const int flag = over ? (int)F_GAME_OVER : 0;
     if (c.cont) {  // next_turn: `return self.game_over, True, True`, then the scan goes on (:609-611)
-        c.done = over | (int)(F_HAND_OVER | F_ROUND_OVER);
+        c.done = flag | (int)(F_HAND_OVER | F_ROUND_OVER);
         if (over) c.pc = PC_DONE;
         else seat_scan<P>(v, s, x, m, c);
     } else {  // :619
-        c.done = over | (int)F_HAND_OVER;
+        c.done = flag | (int)F_HAND_OVER;
         c.pc = PC_DONE;
     }
+    return reset_now;
 }
 
 }  // namespace pkb

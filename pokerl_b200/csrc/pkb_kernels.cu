@@ -30,6 +30,7 @@ struct DevState {
     uint32_t *meta, *hand, *episode;
     unsigned long long* stats;  // [STAT_COUNT] counters
     double* payoff_sum;         // [MAX_PLAYERS]
+    uint32_t* sched;            // [2] step kernel: next tile to hand out, blocks that have finished
     uint64_t n, stride;
 };
 
@@ -48,18 +49,44 @@ struct StepArgs {
     uint32_t num_tiles;
 };
 
-constexpr int STRIDE_ALIGN = 1024;  // env-count granularity of the HBM planes: a multiple of every tile size
-constexpr int STEP_THREADS = 256;   // block size of the step kernel
-#ifndef PKB_STEP_MIN_BLOCKS
-#define PKB_STEP_MIN_BLOCKS 3
+// ---- tuning knobs of the step kernel (defaults: the measured best on B200) ----
+#ifndef PKB_TILE_SMALL
+#define PKB_TILE_SMALL 512     // envs per tile for P <= 4
 #endif
+#ifndef PKB_TILE_LARGE
+#define PKB_TILE_LARGE 128     // envs per tile for P >= 5
+#endif
+#ifndef PKB_THREADS_SMALL
+#define PKB_THREADS_SMALL 256  // block size for P <= 4
+#endif
+#ifndef PKB_THREADS_LARGE
+#define PKB_THREADS_LARGE 128  // block size for P >= 5
+#endif
+#ifndef PKB_MIN_BLOCKS_SMALL
+#define PKB_MIN_BLOCKS_SMALL 3  // resident blocks per SM the kernel is compiled for (register cap), P <= 4
+#endif
+#ifndef PKB_MIN_BLOCKS_LARGE
+#define PKB_MIN_BLOCKS_LARGE 4  // the same for P >= 5
+#endif
+constexpr int STRIDE_ALIGN = 1024;  // env-count granularity of the HBM planes: a multiple of every tile size
+static_assert(STRIDE_ALIGN % PKB_TILE_SMALL == 0 && STRIDE_ALIGN % PKB_TILE_LARGE == 0, "tiles must divide the plane stride");
 
 // envs per tile: the tile (78 B per heads-up env, 278 B per ten-player env) stays well below 1/3 of
 // the 227 KB of shared memory so that three blocks are resident per SM
 template <int P>
+__host__ __device__ constexpr int step_threads()
+{
+    return P <= 4 ? PKB_THREADS_SMALL : PKB_THREADS_LARGE;
+}
+template <int P>
+__host__ __device__ constexpr int step_min_blocks()
+{
+    return P <= 4 ? PKB_MIN_BLOCKS_SMALL : PKB_MIN_BLOCKS_LARGE;
+}
+template <int P>
 __host__ __device__ constexpr int tile_envs()
 {
-    return P <= 4 ? 512 : 256;
+    return P <= 4 ? PKB_TILE_SMALL : PKB_TILE_LARGE;
 }
 
 PKB_D View<0> global_view(const DevState& d)
@@ -68,24 +95,30 @@ PKB_D View<0> global_view(const DevState& d)
 }
 
 // ---- shared-memory tile: [field][slot] rows in the same order and element types as the HBM
-// planes, so each row is ONE contiguous bulk copy in either direction -------------------------
+// planes, so each row is ONE contiguous bulk copy in either direction.  A block holds NBUF such
+// buffers (the tile being stepped and the next one in flight) plus one set of work lists. -------------
 template <int P>
 struct Tile {
     static constexpr int T = tile_envs<P>();
-    static constexpr int ROWS = 4 * P + 3;  // 3P f64 seat rows, mr, meta, hand, P state rows
-    static constexpr size_t OFF_BAR = 0;    // mbarrier (8 B) + list counters (2 x u32)
-    static constexpr size_t OFF_CR = 16;
+    static constexpr int NBUF = 2;
+    static constexpr int ROWS = 4 * P + 3;       // rows stored back: 3P f64 seat rows, mr, meta, hand, P state rows
+    static constexpr int LOAD_ROWS = ROWS + 1;   // + the episode counters (read-only in the tile: the deal replay is keyed by them)
+    // offsets inside one buffer
+    static constexpr size_t OFF_CR = 0;
     static constexpr size_t OFF_BT = OFF_CR + (size_t)P * T * 8;
     static constexpr size_t OFF_PD = OFF_BT + (size_t)P * T * 8;
     static constexpr size_t OFF_MR = OFF_PD + (size_t)P * T * 8;
     static constexpr size_t OFF_META = OFF_MR + (size_t)T * 8;
     static constexpr size_t OFF_HAND = OFF_META + (size_t)T * 4;
     static constexpr size_t OFF_ST = OFF_HAND + (size_t)T * 4;
-    static constexpr size_t OFF_CTL = OFF_ST + (size_t)P * T;      // u32 control word of parked slots
-    static constexpr size_t OFF_LIST_E = OFF_CTL + (size_t)T * 4;  // u16 slots whose hand ended
+    static constexpr size_t OFF_EP = (OFF_ST + (size_t)P * T + 15) / 16 * 16;  // u32 episode counters
+    static constexpr size_t BUF_BYTES = (OFF_EP + (size_t)T * 4 + 127) / 128 * 128;
+    // block layout: header (mbarriers, list counters) | NBUF buffers | ctl | list E | list S
+    static constexpr size_t HEADER = 128;
+    static constexpr size_t OFF_CTL = HEADER + NBUF * BUF_BYTES;      // u32 control word of parked slots
+    static constexpr size_t OFF_LIST_E = OFF_CTL + (size_t)T * 4;     // u16 slots whose hand ended
     static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 2;  // u16 slots that need a ranked showdown
     static constexpr size_t BYTES = OFF_LIST_S + (size_t)T * 2;
-    static constexpr uint32_t TX_BYTES = (uint32_t)((3 * P + 1) * T * 8 + 2 * T * 4 + P * T);
 };
 
 PKB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,11 +138,11 @@ PKB_D void mbar_wait(uint32_t bar, uint32_t parity)
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+        "}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");  // suspend-time hint (ns): do not spin on issue slots
 }
 // TMA 1-D bulk copies (SASS: UBLKCP); sizes and addresses are multiples of 16 bytes
 PKB_D void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
@@ -128,7 +161,7 @@ PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::
 PKB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 PKB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// row r of the tile: where it lives in HBM (for the tile that starts at env `base`) and in shared memory
+// row r of a tile: where it lives in HBM (for the tile that starts at env `base`) and inside a tile buffer
 template <int P>
 PKB_D void tile_row(const DevState& d, size_t base, int r, char*& gptr, uint32_t& soff, uint32_t& bytes)
 {
@@ -152,11 +185,15 @@ PKB_D void tile_row(const DevState& d, size_t base, int r, char*& gptr, uint32_t
         gptr = reinterpret_cast<char*>(d.hand + base);
         soff = (uint32_t)L::OFF_HAND;
         bytes = T * 4;
-    } else {
+    } else if (r < L::ROWS) {
         const int seat = r - (3 * P + 3);
         gptr = reinterpret_cast<char*>(d.st + (size_t)seat * d.stride + base);
         soff = (uint32_t)(L::OFF_ST + (size_t)seat * T);
         bytes = T;
+    } else {
+        gptr = reinterpret_cast<char*>(d.episode + base);
+        soff = (uint32_t)L::OFF_EP;
+        bytes = T * 4;
     }
 }
 
@@ -205,34 +242,6 @@ PKB_D uint32_t write_outputs(const V& v, int s, const Ctl& c, const StepArgs& a,
     return f;
 }
 
-// What follows Game.end_hand once the payoffs are in the pending plane (game.py:530-539 and the
-// caller's use of the return value), then Game.reset() if the game ended and auto-reset is on.
-// Leaves c.pc == PC_END_HAND when ANOTHER hand ends inside the same step (rare: all-in blinds).
-template <int P, class V>
-PKB_D void finish_hand(V& v, int s, Seats& x, Meta& m, Ctl& c, const StepArgs& a, size_t env, Tally<P>& tl)
-{
-    const DevState& d = a.d;
-    double pay[P];
-    end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc);
-#pragma unroll
-    for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
-    if (c.pc == PC_DONE && (c.done & (int)F_GAME_OVER) && !c.poisoned && a.gc.auto_reset) {
-        d.episode[env] += 1;  // Game.reset() right after the step that ended the game (game.py:397-412)
-        reset_env<P>(v, s, x, m, a.gc);
-    }
-}
-
-// game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
-// reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED.
-template <int P>
-PKB_D void assert_exit(const Seats& x, Ctl& c, const StepArgs& a, size_t env)
-{
-#pragma unroll
-    for (int p = 0; p < P; ++p) a.d.payoffs[p * a.d.stride + env] = 0.0;
-    c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
-    c.pc = PC_DONE;
-}
-
 // block reduction of the per-thread tallies into the handle's statistics
 template <int P>
 PKB_D void reduce_stats(const DevState& d, const Tally<P>& tl)
@@ -263,66 +272,141 @@ PKB_D void reduce_stats(const DevState& d, const Tally<P>& tl)
 }
 
 // --------------------------------------------------------------------------------------------
-// Game.step (game.py:621-700) on every env.  A persistent block walks tiles of T envs; a tile's
-// plane rows are pulled into shared memory by TMA bulk copies, stepped in place, and pushed back,
-// so each env's state crosses HBM exactly once in each direction per step.
-// The branches of a step differ by 10-100x in cost (a bet; a hand that ends; a ranked showdown),
-// so instead of letting warps diverge the block runs three phases over the tile, handing the
-// expensive cases on through compacted slot lists so that each phase runs at full warp width:
-//   A  every slot:          validate/sample the action, bet, seat scan, next_turn commits  -> list E
-//   B  slots in list E:     end_hand: commit, last-stand pots, set up the next hand, resume -> list S
-//   C  slots in list S:     ranked showdown (deal replay, 7-card ranks, side pots), then as B
+// Game.step (game.py:621-700) on every env: ONE persistent kernel.
+//
+// A block walks tiles of T envs.  A tile's plane rows are pulled into a shared-memory buffer by TMA
+// bulk copies (the next tile is prefetched into the other buffer while this one is stepped), stepped
+// in place, and pushed back by TMA bulk copies, so each env's state crosses HBM exactly once in each
+// direction per step.
+//
+// The branches of a step differ by 10-100x in cost (a bet; a hand that ends: ~1/3 of heads-up steps;
+// a ranked showdown: ~1/8), and with 32 envs per warp every warp would execute all of them.  So the
+// work is split into three passes over the tile that hand the expensive cases on through compacted
+// slot lists, each pass running at full warp width:
+//   A  every slot:       validate/sample the action, bet, seat scan, next_turn commits; when the hand
+//                        ends also end_hand's head (commit, last-stand pot)       -> list E (+ list S)
+//   C  slots in list S:  the ranked showdown (deal replay, 7-card ranks, side pots)
+//   D  slots in list E:  end_hand's tail (payoffs, BROKEN seats, auto-reset, next hand's blinds), the
+//                        resumed seat scan and the step's outputs
 // --------------------------------------------------------------------------------------------
-template <int P, bool SAMPLE>
-__global__ void __launch_bounds__(STEP_THREADS, PKB_STEP_MIN_BLOCKS) step_tile_kernel(const __grid_constant__ StepArgs a)
+#ifdef PKB_TIMING
+__device__ unsigned long long g_span[3] = {~0ull, 0ull, 0ull};  // globaltimer: earliest block start, latest block start, latest block end
+__device__ unsigned long long g_blk[2048][4];  // per block of the last launch: start ns, end ns, SM id, tiles
+__device__ unsigned long long g_timing[8];  // cycles as seen by thread 0: load wait, A, C, D, store issue, whole block, tiles
+#define PKB_TICK(i)                                        \
+    do {                                                   \
+        if (tid == 0) {                                    \
+            const long long now_ = clock64();              \
+            tacc[i] += (unsigned long long)(now_ - tlast); \
+            tlast = now_;                                  \
+        }                                                  \
+    } while (0)
+#else
+#define PKB_TICK(i)
+#endif
+
+// The rare rest of a step in which ANOTHER hand ends (all-in blinds): whole hands, one after the
+// other, until the step is done.  Out of line: it is a second copy of passes A-tail, C and D.
+template <int P>
+__device__ __noinline__ void run_further_hands(unsigned char* buf, uint32_t* ctl, const uint32_t* ep, int s, size_t env,
+                                               const StepArgs& a)
 {
     using L = Tile<P>;
-    constexpr int T = L::T;
+    View<L::T> v = tile_view<P>(buf);
+    const DevState& d = a.d;
+    Seats x = load_seats<P>(v, s);
+    Ctl c = unpack_ctl(ctl[s]);
+    Meta m = unpack_meta(v.meta[s]);
+    uint32_t episode = ep[s];
+    unsigned long long hands = 0, shows = 0;
+    while (c.pc == PC_END_HAND) {
+        ++hands;
+        const bool ranked = end_hand_begin<P>(v, s, x, c);
+        if (!ranked && c.poisoned) break;
+        if (ranked) {
+            ++shows;
+            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode);
+        }
+        c.pc = PC_DONE;
+        double pay[P];
+        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) d.episode[env] = ++episode;
+        if (a.gc.track_stats)
+            for (int p = 0; p < P; ++p) atomicAdd(&d.payoff_sum[p], pay[p]);
+    }
+    if (a.gc.track_stats) {
+        atomicAdd(&d.stats[STAT_HANDS], hands);
+        atomicAdd(&d.stats[STAT_SHOWDOWNS], shows);
+    }
+    store_seats<P>(v, s, x);
+    v.meta[s] = pack_meta(m);
+    ctl[s] = pack_ctl(c);
+}
+
+template <int P, bool SAMPLE>
+__global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_tile_kernel(const __grid_constant__ StepArgs a)
+{
+    using L = Tile<P>;
+    constexpr int T = L::T, NBUF = L::NBUF, STEP_THREADS = step_threads<P>();
+    static_assert(T % STEP_THREADS == 0 && L::LOAD_ROWS <= STEP_THREADS, "tile / block shape");
     extern __shared__ __align__(128) unsigned char smem[];
-    View<T> v = tile_view<P>(smem);
     uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + L::OFF_CTL);
     uint16_t* list_e = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST_E);
     uint16_t* list_s = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST_S);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L::OFF_BAR + 8);
-    const uint32_t bar = smem_u32(smem + L::OFF_BAR), smem_base = smem_u32(smem);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + 8 * NBUF);  // list lengths {E, S}
+    const uint32_t smem_base = smem_u32(smem);
     const DevState& d = a.d;
     const int tid = threadIdx.x;
 
-    if (tid == 0) mbar_init(bar, L::ROWS);
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) mbar_init(smem_base + 8 * b, L::LOAD_ROWS);
+        cnt[0] = cnt[1] = 0;
+    }
     __syncthreads();
+
+    // thread r owns row r of every tile, in both directions
+    auto issue_load = [&](uint32_t tile, int b) {
+        if (tid < L::LOAD_ROWS) {
+            char* g;
+            uint32_t soff, bytes;
+            tile_row<P>(d, (size_t)tile * T, tid, g, soff, bytes);
+            bulk_wait_read();  // this row's last store has left shared memory
+            mbar_arrive_expect_tx(smem_base + 8 * b, bytes);
+            bulk_load(smem_base + (uint32_t)(L::HEADER + b * L::BUF_BYTES) + soff, g, bytes, smem_base + 8 * b);
+        }
+    };
 
     Tally<P> tl;
 #pragma unroll
     for (int p = 0; p < P; ++p) tl.pay[p] = 0.0;
     tl.hands = tl.shows = tl.games = tl.poisoned = tl.invalid = tl.live = 0;
-    uint32_t parity = 0;
+#ifdef PKB_TIMING
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+    const long long tstart = tlast;
+    unsigned long long gt0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
 
-    for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    // tiles are handed out dynamically (one global atomic per tile): blocks that drew cheap tiles take more
+    uint32_t* next_tile = reinterpret_cast<uint32_t*>(smem + 8 * NBUF + 8);  // [2], written by thread 0
+    if (tid == 0) next_tile[0] = atomicAdd(&d.sched[0], 1u);
+    __syncthreads();
+    uint32_t tile = next_tile[0];
+    if (tile < a.num_tiles) issue_load(tile, 0);
+    for (uint32_t it = 0; tile < a.num_tiles; ++it) {
+        const int b = (int)(it % NBUF);
+        unsigned char* buf = smem + L::HEADER + b * L::BUF_BYTES;
+        View<T> v = tile_view<P>(buf);
+        const uint32_t* ep = reinterpret_cast<const uint32_t*>(buf + L::OFF_EP);
         const size_t base = (size_t)tile * T;
-        // ---- load: thread r owns row r in both directions
-        if (tid < L::ROWS) {
-            char* g;
-            uint32_t soff, bytes;
-            tile_row<P>(d, base, tid, g, soff, bytes);
-            bulk_wait_read();  // the previous tile's store of this row has left shared memory
-            if (tid == 0) cnt[0] = cnt[1] = 0;
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_load(smem_base + soff, g, bytes, bar);
-        }
-        // the random words do not depend on the state: draw them while the tile is in flight
-        uint32_t word[T / STEP_THREADS];
-        if (SAMPLE) {
-#pragma unroll
-            for (int e = 0; e < T / STEP_THREADS; ++e)
-                word[e] = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)(base + e * STEP_THREADS + tid), a.step_idx);
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1u;
+        if (tid == 0) next_tile[(it + 1) & 1] = atomicAdd(&d.sched[0], 1u);  // read by everyone after pass A's barrier
+        mbar_wait(smem_base + 8 * b, (it / NBUF) & 1u);
+        PKB_TICK(0);
 
-        // ---- phase A: every slot
-#pragma unroll
-        for (int e = 0; e < T / STEP_THREADS; ++e) {
-            const int s = e * STEP_THREADS + tid;
+        // ---- pass A: every slot (one copy of the body: the hot loop has to stay in the instruction cache)
+#pragma unroll 1
+        for (int s = tid; s < T; s += STEP_THREADS) {
             const size_t env = base + s;
             const bool live = env < d.n;
             Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
@@ -333,86 +417,97 @@ __global__ void __launch_bounds__(STEP_THREADS, PKB_STEP_MIN_BLOCKS) step_tile_k
                 const uint32_t vm = valid_mask_from(hb, credit, v.mr[s]);
                 int action;
                 if (SAMPLE) {
-                    action = a.use_weights ? pick_weighted(word[e], vm, a.weights) : pick_uniform(word[e], vm);
+                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
+                    action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     if (a.actions_out) a.actions_out[env] = action;
                 } else
                     action = a.actions[env];
                 step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
+                ++tl.live;
+                tl.invalid += (uint32_t)c.invalid;
+                if (c.pc == PC_END_HAND) {
+                    // end_hand's head (game.py:453-482) right here: it is short, and it decides the list
+                    ++tl.hands;
+                    if (end_hand_begin<P>(v, s, x, c)) c.pc = PC_SHOWDOWN;
+                    ctl[s] = pack_ctl(c);
+                }
                 if (!c.invalid) {  // an invalid action changes nothing (game.py:649-651)
                     store_seats<P>(v, s, x);
                     v.meta[s] = pack_meta(m);
                 }
-                ++tl.live;
-                tl.invalid += (uint32_t)c.invalid;
-                if (c.pc == PC_END_HAND) ctl[s] = pack_ctl(c);
-                else tl.poisoned += (uint32_t)c.poisoned, write_outputs<P>(v, s, c, a, env);
+                if (c.pc == PC_DONE) {
+                    tl.poisoned += (uint32_t)c.poisoned;
+                    write_outputs<P>(v, s, c, a, env);
+                }
             }
-            list_append(list_e, &cnt[0], live && c.pc == PC_END_HAND, (uint32_t)s);
+            list_append(list_e, &cnt[0], live && c.pc != PC_DONE, (uint32_t)s);
+            list_append(list_s, &cnt[1], live && c.pc == PC_SHOWDOWN, (uint32_t)s);
         }
         __syncthreads();
+        PKB_TICK(1);
+        // the other buffer is free (its stores were issued before pass A): prefetch the next tile into it
+        const uint32_t tile_after = next_tile[(it + 1) & 1];
+        if (tile_after < a.num_tiles) issue_load(tile_after, b ^ 1);
 
-        // ---- phase B: end_hand for the slots in list E
+        // both list lengths are read here, so that thread 0 can clear the counters after the next barrier
+#if defined(PKB_DEBUG_SKIP)
+        const uint32_t n_s = 0;  // timing experiment only: results are wrong
+#else
+        const uint32_t n_s = cnt[1];
+#endif
+#if defined(PKB_DEBUG_SKIP) && PKB_DEBUG_SKIP == 1
+        const uint32_t n_e = 0;  // timing experiment only: results are wrong
+#else
         const uint32_t n_e = cnt[0];
+#endif
+
+        // ---- pass C: the ranked showdown for the slots in list S
+        for (uint32_t i = tid; i < n_s; i += STEP_THREADS) {
+            const int s = list_s[i];
+            const Seats x = load_seats<P>(v, s);
+            const Ctl c = unpack_ctl(ctl[s]);
+            ++tl.shows;
+            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+        }
+        __syncthreads();
+        PKB_TICK(2);
+        if (tid == 0) cnt[0] = cnt[1] = 0;  // every thread has read them; the next pass A is two barriers away
+
+        // ---- pass D: the rest of end_hand and of the step for the slots in list E
         for (uint32_t i = tid; i < n_e; i += STEP_THREADS) {
             const int s = list_e[i];
             const size_t env = base + s;
             Seats x = load_seats<P>(v, s);
             Ctl c = unpack_ctl(ctl[s]);
             Meta m = unpack_meta(v.meta[s]);
-            bool to_c = false;
-            ++tl.hands;
-            if (end_hand_begin<P>(v, s, x, c)) {
-                c.pc = PC_SHOWDOWN;
-                to_c = true;
-            } else if (c.poisoned) {
-                assert_exit<P>(x, c, a, env);
+            if (c.poisoned) {
+                // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
+                // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED
+#pragma unroll
+                for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
+                c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
+                c.pc = PC_DONE;
             } else {
-                finish_hand<P>(v, s, x, m, c, a, env, tl);
-                to_c = c.pc == PC_END_HAND;  // another hand ends inside this step: phase C runs it
-            }
-            v.meta[s] = pack_meta(m);
-            store_seats<P>(v, s, x);
-            if (to_c) ctl[s] = pack_ctl(c);
-            else {
-                const uint32_t f = write_outputs<P>(v, s, c, a, env);
-                tl.games += (f & F_GAME_OVER) ? 1u : 0u;
-                tl.poisoned += (uint32_t)c.poisoned;
-            }
-            list_append(list_s, &cnt[1], to_c, (uint32_t)s);
-        }
-        __syncthreads();
-
-        // ---- phase C: ranked showdowns (and the rare further hands of a step) for the slots in list S
-        const uint32_t n_s = cnt[1];
-        for (uint32_t i = tid; i < n_s; i += STEP_THREADS) {
-            const int s = list_s[i];
-            const size_t env = base + s;
-            Seats x = load_seats<P>(v, s);
-            Ctl c = unpack_ctl(ctl[s]);
-            Meta m = unpack_meta(v.meta[s]);
-            const uint32_t episode = d.episode[env];
-            bool asserted = false;
-            while (c.pc != PC_DONE) {
-                bool ranked = c.pc == PC_SHOWDOWN;
-                if (!ranked) {  // PC_END_HAND: a further hand of this step, from its beginning
-                    ++tl.hands;
-                    ranked = end_hand_begin<P>(v, s, x, c);
-                    if (!ranked && c.poisoned) {
-                        asserted = true;
-                        break;
+                c.pc = PC_DONE;
+                double pay[P];
+                if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) d.episode[env] = ep[s] + 1;
+#pragma unroll
+                for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
+                store_seats<P>(v, s, x);
+                v.meta[s] = pack_meta(m);
+                if (c.pc == PC_END_HAND) {  // another hand ends inside this step
+                    ctl[s] = pack_ctl(c);
+                    run_further_hands<P>(buf, ctl, ep, s, env, a);
+                    c = unpack_ctl(ctl[s]);
+                    if (c.poisoned) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
+                        x = load_seats<P>(v, s);
+                        c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
+                        c.pc = PC_DONE;
                     }
                 }
-                if (ranked) {
-                    ++tl.shows;
-                    showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode,
-                                [](uint64_t mask) { return eval_mask52(mask); });
-                }
-                c.pc = PC_DONE;
-                finish_hand<P>(v, s, x, m, c, a, env, tl);
             }
-            if (asserted) assert_exit<P>(x, c, a, env);
-            v.meta[s] = pack_meta(m);
-            store_seats<P>(v, s, x);
             const uint32_t f = write_outputs<P>(v, s, c, a, env);
             tl.games += (f & F_GAME_OVER) ? 1u : 0u;
             tl.poisoned += (uint32_t)c.poisoned;
@@ -421,15 +516,55 @@ __global__ void __launch_bounds__(STEP_THREADS, PKB_STEP_MIN_BLOCKS) step_tile_k
         // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
         fence_async_smem();
         __syncthreads();
+        PKB_TICK(3);
+#ifdef PKB_PLAIN_STORE
+        for (int r = 0; r < L::ROWS; ++r) {  // experiment: plain 128-bit coalesced stores instead of TMA
+            char* g;
+            uint32_t soff, bytes;
+            tile_row<P>(d, base, r, g, soff, bytes);
+            for (uint32_t o = tid * 16; o < bytes; o += STEP_THREADS * 16)
+                *reinterpret_cast<uint4*>(g + o) = *reinterpret_cast<const uint4*>(buf + soff + o);
+        }
+#else
         if (tid < L::ROWS) {
             char* g;
             uint32_t soff, bytes;
             tile_row<P>(d, base, tid, g, soff, bytes);
-            bulk_store(g, smem_base + soff, bytes);
+            bulk_store(g, smem_base + (uint32_t)(L::HEADER + b * L::BUF_BYTES) + soff, bytes);
             bulk_commit();
         }
+#endif
+        PKB_TICK(4);
+#ifdef PKB_TIMING
+        if (tid == 0) tacc[6] += 1;
+#endif
+        tile = tile_after;
     }
     if (tid < L::ROWS) bulk_wait_all();
+    if (tid == 0 && atomicAdd(&d.sched[1], 1u) == gridDim.x - 1) {  // the last block to finish re-arms the scheduler
+        d.sched[0] = 0;
+        d.sched[1] = 0;
+    }
+#ifdef PKB_TIMING
+    if (tid == 0) {
+        tacc[5] = (unsigned long long)(clock64() - tstart);
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        for (int i = 0; i < 7; ++i) atomicAdd(&g_timing[i], tacc[i]);
+        atomicAdd(&g_timing[7], gt1 - gt0);  // nanoseconds
+        if (blockIdx.x < 2048) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_blk[blockIdx.x][0] = gt0;
+            g_blk[blockIdx.x][1] = gt1;
+            g_blk[blockIdx.x][2] = smid;
+            g_blk[blockIdx.x][3] = tacc[6];
+        }
+        atomicMin(&g_span[0], gt0);
+        atomicMax(&g_span[1], gt0);
+        atomicMax(&g_span[2], gt1);
+    }
+#endif
     if (a.gc.track_stats) reduce_stats<P>(d, tl);
 }
 
@@ -691,19 +826,41 @@ static cudaError_t launch_step(const StepArgs& a, cudaStream_t s, int device, in
     if (!blocks_per_sm[device]) {
         cudaError_t e = cudaFuncSetAttribute(step_tile_kernel<P, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // the tile ring wants (almost) all of the SM's 228 KB as shared memory; without this the driver may pick a
+        // smaller carve-out, fewer blocks become resident than the persistent grid assumes, and the rest run as a second wave
+        e = cudaFuncSetAttribute(step_tile_kernel<P, SAMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_tile_kernel<P, SAMPLE>, STEP_THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_tile_kernel<P, SAMPLE>, step_threads<P>(), smem);
         if (e != cudaSuccess) return e;
         if (nb < 1) return cudaErrorLaunchOutOfResources;
         blocks_per_sm[device] = nb;
     }
+    if (getenv("PKB_VERBOSE")) fprintf(stderr, "pkb: step kernel P=%d smem=%zu blocks/SM=%d\n", P, smem, blocks_per_sm[device]);
     const unsigned resident = (unsigned)(blocks_per_sm[device] * sm_count);
     const unsigned grid = a.num_tiles < resident ? a.num_tiles : resident;
-    step_tile_kernel<P, SAMPLE><<<grid, STEP_THREADS, smem, s>>>(a);
+    step_tile_kernel<P, SAMPLE><<<grid, step_threads<P>(), smem, s>>>(a);
     return cudaGetLastError();
 }
 
 extern "C" {
+
+#ifdef PKB_TIMING
+// debug builds only: read and clear the phase cycle counters of the step kernel
+int pkb_debug_timing(unsigned long long* out)
+{
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out, g_timing, sizeof zero) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(g_timing, zero, sizeof zero) == cudaSuccess ? 0 : -1;
+}
+int pkb_debug_blocks(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_blk, sizeof(unsigned long long) * 2048 * 4) == cudaSuccess ? 0 : -1; }
+int pkb_debug_span(unsigned long long* out)
+{
+    const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+    if (cudaMemcpyFromSymbol(out, g_span, sizeof init) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(g_span, init, sizeof init) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 const char* pkb_last_error(void) { return g_error.c_str(); }
 int pkb_abi_version(void) { return PKB_ABI_VERSION; }
@@ -736,7 +893,7 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     // arena: f64 planes | u32 planes | u8 planes | stats
     const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)3 * stride, n_u8 = (size_t)P * stride;
     const size_t off_u32 = n_f64 * 8, off_u8 = off_u32 + n_u32 * 4, off_stats = (off_u8 + n_u8 + 255) / 256 * 256;
-    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4;
+    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 2 * 4;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) {
         delete h;
@@ -764,6 +921,7 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     d.stats = reinterpret_cast<unsigned long long*>(base + off_stats);
     d.payoff_sum = reinterpret_cast<double*>(base + off_stats + STAT_COUNT * 8);
     h->d_weights = reinterpret_cast<uint32_t*>(base + off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8);
+    d.sched = h->d_weights + NUM_MOVES + 1;
     d.n = n;
     d.stride = stride;
 

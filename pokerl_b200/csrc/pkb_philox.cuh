@@ -22,7 +22,7 @@ struct U4 {
     uint32_t x, y, z, w;
 };
 
-PKB_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+PKB_HD_CALL U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -36,7 +36,7 @@ PKB_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
 }
 
 // position of the j-th (0-based) set bit of a 52-bit mask; j < popcount(f)
-PKB_HD uint32_t select_bit(uint64_t f, uint32_t j)
+PKB_HD_CALL uint32_t select_bit(uint64_t f, uint32_t j)
 {
     uint32_t w = (uint32_t)f, pos = 0;
     uint32_t c = (uint32_t)popc32(w);

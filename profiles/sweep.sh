@@ -1,0 +1,8 @@
+#!/bin/bash
+# Runs the parity check and the device-time probe for every library under pokerl_b200/_lib/variants/.
+for lib in pokerl_b200/_lib/variants/*.so; do
+  export PKB_LIB=$PWD/$lib
+  timeout 120 python profiles/parity_quick.py 2>&1 | tail -1
+  timeout 120 python profiles/quick_step_bench.py --steps 100 2>&1 | tail -1
+  if [ -n "$SWEEP_P9" ]; then timeout 120 python profiles/quick_step_bench.py --steps 50 --players 9 2>&1 | tail -1; fi
+done
