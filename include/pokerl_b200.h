@@ -41,8 +41,13 @@ extern "C" {
 #define PKB_F_GAME_OVER 1u   /* Game.step()[0], game.py:565, 619 */
 #define PKB_F_HAND_OVER 2u   /* Game.step()[1] */
 #define PKB_F_ROUND_OVER 4u  /* Game.step()[2] */
+#define PKB_F_SKIPPED 32u    /* the action was PKB_ACTION_SKIP: env untouched, not counted (masked lockstep advance) */
 #define PKB_F_INVALID 64u    /* action not in valid_actions: env untouched (ValueError at game.py:649-651) */
 #define PKB_F_POISONED 128u  /* reference would not terminate (game.py:607) or would assert (game.py:473) */
+
+/* pkb_step action value that leaves an env alone: lets a caller advance only SOME envs of a batch, e.g. the
+ * "step the opponents until the agent's seat is active" loops of PokerGameEnv (envs/game_env.py:24-27, 41-52) */
+#define PKB_ACTION_SKIP (-2147483647 - 1)
 
 #define PKB_NEXT_TURN_CAP 64 /* next_turn() calls allowed inside one step before PKB_F_POISONED */
 

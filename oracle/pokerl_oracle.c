@@ -745,7 +745,7 @@ void ora_batch_step(ora_batch *b, const int32_t *actions, uint8_t *flags, uint8_
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)b->n; ++i) {
         ora_game *g = &b->games[i];
-        unsigned f = step_one(b, g, actions[i]);
+        unsigned f = actions[i] == ORA_ACTION_SKIP ? ORA_F_SKIPPED : step_one(b, g, actions[i]);
         if (flags) flags[i] = (uint8_t)f;
         if (valid) valid[i] = (uint8_t)ora_game_valid_mask(g, -1);
     }

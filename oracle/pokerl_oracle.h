@@ -32,7 +32,8 @@ enum { ORA_FOLDED = 0, ORA_ACTIVE = 1, ORA_CALLED = 2, ORA_ALL_IN = 3, ORA_BROKE
 /* enums.py:104-111 */
 enum { ORA_FOLD = 0, ORA_CHECK = 1, ORA_CALL = 2, ORA_RAISE_TEN = 3, ORA_RAISE_QUARTER = 4, ORA_RAISE_HALF = 5, ORA_MOVE_ALL_IN = 6 };
 /* step flag bits (this repo's ABI, mirrored by the CUDA path) */
-enum { ORA_F_GAME_OVER = 1, ORA_F_HAND_OVER = 2, ORA_F_ROUND_OVER = 4, ORA_F_INVALID = 64, ORA_F_POISONED = 128 };
+enum { ORA_F_GAME_OVER = 1, ORA_F_HAND_OVER = 2, ORA_F_ROUND_OVER = 4, ORA_F_SKIPPED = 32, ORA_F_INVALID = 64, ORA_F_POISONED = 128 };
+#define ORA_ACTION_SKIP (-2147483647 - 1) /* ora_batch_step leaves that env alone (masked lockstep advance) */
 
 #define ORA_NEXT_TURN_CAP 64
 

@@ -15,6 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libpokerl_oracle.so")
 
 MAX_PLAYERS = 23
 F_GAME_OVER, F_HAND_OVER, F_ROUND_OVER, F_INVALID, F_POISONED = 1, 2, 4, 64, 128
+F_SKIPPED, ACTION_SKIP = 32, -2 ** 31
 
 
 def build(force: bool = False) -> str:

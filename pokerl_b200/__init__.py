@@ -10,6 +10,7 @@ from .judger import eval_hand
 from .cards import Card, create_default_deck
 from .enums import PokerMoves, HandRanking
 from .batch import GameBatch
+from . import agents, envs  # noqa: E402  (pokerl.envs / pokerl.agents)
 
 __version__ = "0.1.0"
 __all__ = ["Game", "GameBatch", "eval_hand", "Card", "create_default_deck", "PokerMoves", "HandRanking"]

@@ -13,6 +13,7 @@ MAX_PLAYERS = 10
 NUM_MOVES = 7
 
 F_GAME_OVER, F_HAND_OVER, F_ROUND_OVER, F_INVALID, F_POISONED = 1, 2, 4, 64, 128
+F_SKIPPED, ACTION_SKIP = 32, -2 ** 31  # PKB_F_SKIPPED, PKB_ACTION_SKIP
 NEXT_TURN_CAP = 64
 
 

@@ -19,7 +19,8 @@
 
 namespace pkb {
 
-constexpr uint32_t F_GAME_OVER = 1u, F_HAND_OVER = 2u, F_ROUND_OVER = 4u, F_INVALID = 64u, F_POISONED = 128u;
+constexpr uint32_t F_GAME_OVER = 1u, F_HAND_OVER = 2u, F_ROUND_OVER = 4u, F_SKIPPED = 32u, F_INVALID = 64u, F_POISONED = 128u;
+constexpr int ACTION_SKIP = -2147483647 - 1;
 constexpr int NEXT_TURN_CAP = 64;
 constexpr int MAX_PLAYERS = 10;
 

@@ -234,9 +234,9 @@ struct Tally {
 
 // Step outputs of one finished env: flag bits and the valid mask of the new active player
 template <int P, class V>
-PKB_D uint32_t write_outputs(const V& v, int s, const Ctl& c, const StepArgs& a, size_t env)
+PKB_D uint32_t write_outputs(const V& v, int s, const Ctl& c, const StepArgs& a, size_t env, bool skipped = false)
 {
-    const uint32_t f = (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
+    const uint32_t f = skipped ? F_SKIPPED : (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
     if (a.flags) a.flags[env] = (uint8_t)f;
     if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(v, s, unpack_meta(v.meta[s]).act);
     return f;
@@ -423,8 +423,9 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
                 } else
                     action = a.actions[env];
                 step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
-                ++tl.live;
-                tl.invalid += (uint32_t)c.invalid;
+                const bool skipped = !SAMPLE && action == ACTION_SKIP;  // rejected like any out-of-range action, but not an error
+                tl.live += skipped ? 0u : 1u;
+                tl.invalid += skipped ? 0u : (uint32_t)c.invalid;
                 if (c.pc == PC_END_HAND) {
                     // end_hand's head (game.py:453-482) right here: it is short, and it decides the list
                     ++tl.hands;
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
                 }
                 if (c.pc == PC_DONE) {
                     tl.poisoned += (uint32_t)c.poisoned;
-                    write_outputs<P>(v, s, c, a, env);
+                    write_outputs<P>(v, s, c, a, env, skipped);
                 }
             }
             list_append(list_e, &cnt[0], live && c.pc != PC_DONE, (uint32_t)s);

@@ -157,3 +157,28 @@ def test_cards_and_enums_mirror_reference():
     assert (PlayerState.FOLDED, PlayerState.BROKEN) == (0, 4) and CardRank.ACE == 13
     with pytest.raises(AssertionError):
         Card(0x4f)
+
+
+def test_env_and_agent_api_mirror_reference():
+    """pokerl.envs / pokerl.agents names (pokerl/envs/__init__.py:1-2, agents/__init__.py:1-3) exist, the random
+    agent keeps the reference's scalar behaviour, and the env refuses to run without a GPU (no CPU fallback)."""
+    import numpy as np
+    import pokerl_b200
+    from pokerl_b200 import _native as nat
+    from pokerl_b200.agents import PokerAgent, RandomAgent
+    from pokerl_b200.envs import PokerEnv, PokerGameEnv
+    assert issubclass(PokerGameEnv, PokerEnv) and issubclass(RandomAgent, PokerAgent)
+    assert pokerl_b200.envs.PokerGameEnv is PokerGameEnv
+
+    class S:
+        valid_actions = np.array([1., 0., 1., 0., 0., 0., 1.])
+    picks = {RandomAgent()(S()) for _ in range(200)}
+    assert picks == {0, 2, 6}
+    assert {RandomAgent(weights=[0, 5, 5, 5, 5, 5, 1])(S()) for _ in range(200)} == {2, 6}
+    for cls in (PokerEnv, PokerAgent):
+        with pytest.raises(NotImplementedError):
+            (cls().reset() if cls is PokerEnv else cls()(None))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(nat.PkbError):
+            PokerGameEnv(agents=[RandomAgent()] * 3, num_players=4)
