@@ -95,6 +95,89 @@ PKB_HD_CALL uint32_t eval_mask52(uint64_t m)
     return (HR_HIGH << 20) | pack_top(any, 5, 0);  // :99
 }
 
+// ---- table-driven form of eval_mask52 (the batch kernels: tables staged in shared memory) ------------
+//
+// One 8192-entry table indexed by a 13-bit rank set x (bit i = rank i+1) answers everything the
+// evaluator asks of a rank set.  Entry layout:
+//   bits  0-19  the up-to-five highest ranks of x as nibbles, highest first (pack_top(x, 5, 0))
+//   bits 20-22  n5 = min(popcount(x), 5)
+//   bits 23-26  high rank of the best 5-long run of consecutive ranks in x (0: none; the wheel is not a run)
+//   bits 27-30  popcount(x)
+// eval_mask52_tbl is branch-free: every category's value is formed with selects and the one with the
+// highest priority (the order of judger.py:83-99) wins.  It returns exactly eval_mask52(m).
+constexpr int EVAL_TABLE_SIZE = 8192;
+
+PKB_HD uint32_t eval_table_entry(uint32_t x)
+{
+    const uint32_t st5 = x & (x << 1) & (x << 2) & (x << 3) & (x << 4);
+    const int n = popc32(x);
+    return pack_top(x, 5, 0) | (uint32_t)(n < 5 ? n : 5) << 20 | (st5 ? (uint32_t)(topbit32(st5) + 1) : 0u) << 23 |
+           (uint32_t)n << 27;
+}
+
+PKB_HD uint32_t tbl_top(uint32_t e, int k)  // the k highest ranks of the entry's set, as nibbles (fewer if the set is smaller)
+{
+    const int n5 = (int)(e >> 20 & 7u);
+    return (e & 0xFFFFFu) >> (4 * (n5 > k ? n5 - k : 0));
+}
+PKB_HD uint32_t tbl_first(uint32_t e) { return tbl_top(e, 1); }              // highest rank nibble (0 for the empty set)
+PKB_HD uint32_t tbl_second(uint32_t e) { return tbl_top(e, 2) & 0xFu; }      // second highest (valid when popcount >= 2)
+
+PKB_HD uint32_t eval_mask52_tbl(uint64_t m, const uint32_t* __restrict__ tbl)
+{
+    const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
+    const uint32_t any = s0 | s1 | s2 | s3;
+    const uint32_t e0 = tbl[s0], e1 = tbl[s1], e2 = tbl[s2], e3 = tbl[s3], ea = tbl[any];
+
+    // suit X (flush suit, else the lowest-numbered suit present) and its lowest maximal run
+    const bool f0 = (e0 >> 27) >= 5, f1 = (e1 >> 27) >= 5, f2 = (e2 >> 27) >= 5, f3 = (e3 >> 27) >= 5;
+    const uint32_t fl = f0 ? s0 : f1 ? s1 : f2 ? s2 : f3 ? s3 : 0u;
+    const uint32_t efl = f0 ? e0 : f1 ? e1 : f2 ? e2 : e3;
+    const uint32_t sx = fl ? fl : s0 ? s0 : s1 ? s1 : s2 ? s2 : s3;
+    const uint32_t run = sx & ~(sx + (sx & (0u - sx)));
+    const uint32_t erun = tbl[run];
+    const uint32_t st_hi = ea >> 23 & 15u;
+
+    // rank multiplicities, bit-sliced
+    const uint32_t a01 = s0 & s1, x01 = s0 ^ s1, a23 = s2 & s3, x23 = s2 ^ s3;
+    const uint32_t quad = a01 & a23;
+    const uint32_t trip = (a01 & x23) | (x01 & a23);
+    const uint32_t pair = (a01 & ~(s2 | s3)) | (a23 & ~(s0 | s1)) | (x01 & x23);
+    const uint32_t eq = tbl[quad], et = tbl[trip], ep = tbl[pair];
+    const uint32_t q = tbl_first(eq), t = tbl_first(et), t2 = tbl_second(et), p1 = tbl_first(ep), p2 = tbl_second(ep);
+    const bool two_trips = (et >> 27) >= 2, two_pairs = (ep >> 27) >= 2;
+
+    // which ranks still count as kickers, how many of them, and what leads the kicker word
+    const bool c_quad = quad != 0;
+    const bool c_full = !c_quad && trip != 0 && (two_trips || pair != 0);
+    const bool c_flush = !c_quad && !c_full && fl != 0;
+    const bool c_straight = !c_quad && !c_full && !c_flush && st_hi != 0;
+    const bool c_tris = !c_quad && !c_full && !c_flush && !c_straight && trip != 0;
+    const bool c_two = !c_quad && !c_full && !c_flush && !c_straight && !c_tris && two_pairs;
+    const bool c_pair = !c_quad && !c_full && !c_flush && !c_straight && !c_tris && !c_two && pair != 0;
+    const uint32_t lead_bit = c_quad ? 1u << (q - 1) : c_tris ? 1u << (t - 1) : c_two ? (1u << (p1 - 1)) | (1u << (p2 - 1))
+                              : c_pair ? 1u << (p1 - 1) : 0u;
+    const int k = c_quad ? 1 : c_tris ? 2 : c_two ? 1 : c_pair ? 3 : 5;
+    const uint32_t ek = tbl[any & ~lead_bit];
+    const int nk = (int)(ek >> 20 & 7u);
+    const uint32_t kick = tbl_top(ek, k);
+    const int cnt = nk < k ? nk : k;
+    const uint32_t lead = c_quad ? q : c_tris ? t : c_two ? p1 << 4 | p2 : c_pair ? p1 : 0u;
+    uint32_t r = (c_quad ? HR_POKER : c_tris ? HR_TRIS : c_two ? HR_TWO_PAIR : c_pair ? HR_PAIR : HR_HIGH) << 20 |
+                 (lead << (4 * cnt) | kick);
+    r = c_full ? (HR_FULL << 20) | t << 4 | (two_trips ? t2 : p1) : r;      // judger.py:92-93
+    r = c_flush ? (HR_FLUSH << 20) | (efl & 0xFFFFFu) : r;                    // :94
+    r = c_straight ? (HR_STRAIGHT << 20) | st_hi : r;                         // :95
+    // the straight-flush tracker and the two wheel special cases come first (judger.py:83-90)
+    const bool run_is_wheel_low = run == 0xFu;
+    const bool sf = (erun >> 27) >= 5;
+    r = sf ? (HR_STRAIGHT_FLUSH << 20) | tbl_first(erun) : r;
+    const bool wheel = !run_is_wheel_low && st_hi == 0 && (any & 0x1000u) && (any & ~(any + (any & (0u - any)))) == 0xFu;
+    r = wheel ? (HR_STRAIGHT << 20) | 4u : r;
+    r = run_is_wheel_low && (sx & 0x1000u) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;
+    return m == 0 ? PACKED_NONE : r;
+}
+
 // ---- list form (duplicates allowed): the two-sorted-copies scan of judger.py:38-99 ----------------
 
 PKB_HD int cv_rank(uint32_t v) { const int r = (int)(v & 0xfu); return r ? r : 13; }

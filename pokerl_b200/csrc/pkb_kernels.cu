@@ -663,10 +663,42 @@ __global__ void eval_cards_kernel(const uint8_t* __restrict__ cards, int k, uint
     }
 }
 
-__global__ void eval_masks_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __restrict__ out)
+// The rank-set table of pkb_eval.cuh, built once per device and staged in shared memory by the batch evaluators
+__device__ uint32_t g_eval_table[EVAL_TABLE_SIZE];
+
+__global__ void eval_table_init_kernel()
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        out[i] = eval_mask52(masks[i]);
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < EVAL_TABLE_SIZE) g_eval_table[x] = eval_table_entry(x);
+}
+
+PKB_D void stage_eval_table(uint32_t* s_tbl)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(g_eval_table);
+    uint4* dst = reinterpret_cast<uint4*>(s_tbl);
+    for (int i = threadIdx.x; i < EVAL_TABLE_SIZE / 4; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+constexpr int EVAL_THREADS = 256;
+
+// eval_hand on id masks: 8 B in, 4 B out per hand; two hands per thread per trip (128-bit loads, 64-bit stores)
+__global__ void __launch_bounds__(EVAL_THREADS, 6)
+eval_masks_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __restrict__ out)
+{
+    __shared__ __align__(16) uint32_t s_tbl[EVAL_TABLE_SIZE];
+    stage_eval_table(s_tbl);
+    const uint64_t pairs = n / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(masks) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    if (aligned) {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+            const ulonglong2 m = reinterpret_cast<const ulonglong2*>(masks)[i];
+            reinterpret_cast<uint2*>(out)[i] = make_uint2(eval_mask52_tbl(m.x, s_tbl), eval_mask52_tbl(m.y, s_tbl));
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) out[n - 1] = eval_mask52_tbl(masks[n - 1], s_tbl);
+    } else {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = eval_mask52_tbl(masks[i], s_tbl);
+    }
 }
 
 __constant__ uint64_t c_binom[53][8];  // C(n, k) for n <= 52, k <= 7
@@ -699,9 +731,10 @@ eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restri
                        unsigned long long* sums)
 {
     __shared__ unsigned long long s_hist[11], s_sum[2];
+    __shared__ __align__(16) uint32_t s_tbl[EVAL_TABLE_SIZE];
     if (threadIdx.x < 11) s_hist[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_sum[threadIdx.x] = 0;
-    __syncthreads();
+    stage_eval_table(s_tbl);
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t lo = t * EXH_CHUNK;
     unsigned long long cats = 0, sum_a = 0, sum_b = 0;
@@ -709,7 +742,7 @@ eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restri
         const int todo = (int)(count - lo < EXH_CHUNK ? count - lo : EXH_CHUNK);
         uint64_t m = unrank_colex(first + lo, k);
         for (int j = 0; j < todo; ++j) {
-            const uint32_t p = eval_mask52(m);
+            const uint32_t p = eval_mask52_tbl(m, s_tbl);
             if (out) out[lo + j] = p;
             cats += 1ull << (6 * (p >> 20));
             sum_a += p;
@@ -1140,11 +1173,31 @@ int pkb_eval_cards(const uint8_t* cards, int32_t k, uint64_t n, uint32_t* out, v
     return 0;
 }
 
+// builds the evaluator's rank-set table on the current device the first time a batch evaluator runs there
+static cudaError_t ensure_eval_table(cudaStream_t s)
+{
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!ready[dev]) {
+        eval_table_init_kernel<<<EVAL_TABLE_SIZE / 256, 256, 0, s>>>();
+        e = cudaGetLastError();
+        if (e == cudaSuccess) ready[dev] = true;
+    }
+    return e;
+}
+
 int pkb_eval_masks(const uint64_t* masks, uint64_t n, uint32_t* out, void* stream)
 {
     if (n == 0) return 0;
     if (!out || !masks) return fail("pkb_eval_masks: null argument");
-    eval_masks_kernel<<<eval_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(masks, n, out);
+    PKB_CUDA(ensure_eval_table(static_cast<cudaStream_t>(stream)));
+    // persistent grid: six 256-thread blocks per SM (the 32 KB table each), grid-stride over the hands
+    const uint64_t want = (n / 2 + EVAL_THREADS - 1) / EVAL_THREADS;
+    const unsigned grid = (unsigned)(want < 148ull * 6 ? (want ? want : 1) : 148ull * 6);
+    eval_masks_kernel<<<grid, EVAL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(masks, n, out);
     PKB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1176,6 +1229,7 @@ int pkb_eval_exhaustive(int32_t k, uint64_t first, uint64_t count, uint64_t* his
     if (first > total || count > total - first) return fail("pkb_eval_exhaustive: range exceeds C(52,k)");
     PKB_CUDA(ensure_binom());
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(ensure_eval_table(s));
     unsigned long long* d_acc = nullptr;
     PKB_CUDA(cudaMalloc(&d_acc, 13 * 8));
     cudaError_t e = cudaMemsetAsync(d_acc, 0, 13 * 8, s);

@@ -20,6 +20,10 @@ def load():
     L = C.CDLL(SO)
     L.hc_eval_mask.restype = C.c_uint32
     L.hc_eval_mask.argtypes = [C.c_uint64]
+    L.hc_eval_mask_tbl.restype = C.c_uint32
+    L.hc_eval_mask_tbl.argtypes = [C.c_uint64]
+    L.hc_eval_tbl_mismatches.restype = C.c_uint64
+    L.hc_eval_tbl_mismatches.argtypes = [C.c_int, C.c_uint64]
     L.hc_eval_cards.restype = C.c_uint32
     L.hc_eval_cards.argtypes = [C.c_void_p, C.c_int]
     L.hc_eval_cards_literal.restype = C.c_uint32

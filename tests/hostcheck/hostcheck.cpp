@@ -10,6 +10,30 @@
 extern "C" {
 
 uint32_t hc_eval_mask(uint64_t m) { return pkb::eval_mask52(m); }
+// the table-driven form used by the batch kernels (table built with the product's own entry function)
+static const uint32_t* eval_table()
+{
+    static uint32_t tbl[pkb::EVAL_TABLE_SIZE];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t x = 0; x < pkb::EVAL_TABLE_SIZE; ++x) tbl[x] = pkb::eval_table_entry(x);
+        ready = true;
+    }
+    return tbl;
+}
+uint32_t hc_eval_mask_tbl(uint64_t m) { return pkb::eval_mask52_tbl(m, eval_table()); }
+// number of k-card hands (all C(52,k), in increasing mask order) on which the two forms differ
+uint64_t hc_eval_tbl_mismatches(int k, uint64_t count)
+{
+    const uint32_t* tbl = eval_table();
+    uint64_t m = (1ull << k) - 1, bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        bad += pkb::eval_mask52_tbl(m, tbl) != pkb::eval_mask52(m);
+        const uint64_t c = m & -m, r = m + c;
+        m = (((r ^ m) >> 2) / c) | r;
+    }
+    return bad;
+}
 uint32_t hc_eval_cards(const uint8_t* c, int n) { return pkb::eval_cards(c, n); }
 uint32_t hc_eval_cards_literal(const uint8_t* c, int n) { return pkb::eval_cards_literal(c, n); }
 

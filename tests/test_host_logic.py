@@ -43,6 +43,16 @@ def test_product_evaluator_7_sampled(hc, ora):
     assert np.array_equal(out, ora.eval_masks_batch(masks))
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7])
+def test_table_evaluator_equals_bitmask_evaluator(hc, ora, k):
+    """The table-driven, branch-free form used by the batch kernels returns exactly what the bitmask evaluator
+    returns: all C(52,k) hands for k <= 6, the first 8M seven-card hands (the GPU test covers all of them)."""
+    import math
+    count = math.comb(52, k) if k <= 6 else 8_000_000
+    assert hc.hc_eval_tbl_mismatches(k, count) == 0
+    assert hc.hc_eval_mask_tbl(0) == int(ora.eval_masks_batch(np.zeros(1, dtype=np.uint64))[0])
+
+
 def test_product_card_list_paths(hc, ora, golden_dir):
     d = np.load(os.path.join(golden_dir, "eval_vectors.npz"))
     for c, k, p in zip(d["cards"], d["counts"], d["packed"]):
