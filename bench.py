@@ -11,10 +11,16 @@ game over.  One bench "step" = one Game.step on every env = one launch of the fu
 sample+step kernel (pkb::step_tile_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective
 (weak scaling); one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
 
-Timing: W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket.  The
-2^20-env state (86 MB) fits the 126 MB L2, so L2 is flushed (256 MB memset) before every timed
-step and each step is timed with its own CUDA event pair on the launching stream; the device time
-is the sum of the K intervals, the reported time is its max over ranks.
+Timing: W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket, timed with
+one CUDA event pair; the reported time is the max over ranks.  One 2^20-env batch (86 MB of state)
+would fit the 126 MB L2, so each GPU holds THREE such batches (258 MB, "inputs larger than L2") and
+steps them round-robin: every step is one pass of the hot path over one batch of 2^20 envs whose
+state was pushed out of L2 by the steps of the other two batches, i.e. it streams from HBM and back.
+The batches are independent, so each one is stepped on its own CUDA stream: the drain of one step's
+persistent kernel (a few tiles whose envs play several hands inside one step) overlaps the next
+batch's step.  `value` is that whole-job throughput; `roofline.isolated_launch_us` is the duration of
+one step launched alone on one stream (the same three batches, one stream), and `flushed_by_memset` /
+`l2_resident` give the single-batch variants for reference.
 
 Prints ONE JSON line on rank 0.
 """
@@ -32,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(num_players=2, start_credits=100, big_blind=2, small_blind=1, seed=0)
 ENVS_PER_GPU = 1 << 20
+RESIDENT_BATCHES = 3  # 3 x 86 MB of env state per GPU: larger than the 126 MB L2
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -57,7 +64,7 @@ def ncu_traffic(key: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled every 20 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -70,7 +77,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
                  str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -179,7 +186,10 @@ def workload_config(envs_per_gpu, world, note=None):
            "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world, "start_credits": WORKLOAD["start_credits"],
            "blinds": [WORKLOAD["big_blind"], WORKLOAD["small_blind"]], "agents": "uniform random over valid actions, on device",
            "auto_reset": True, "seed": WORKLOAD["seed"], "sharding": f"env-sliced x{world}, no data-path collective",
-           "l2": "flushed (256 MB memset) before every timed step; state is 86 MB < 126 MB L2"}
+           "resident_batches_per_gpu": RESIDENT_BATCHES,
+           "l2": f"inputs larger than L2: {RESIDENT_BATCHES} batches of {envs_per_gpu} envs per GPU "
+                 f"({RESIDENT_BATCHES * 86 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2) stepped round-robin, "
+                 "one batch per step"}
     if note:
         cfg["note"] = note
     return cfg
@@ -202,79 +212,149 @@ def run_ours(args, rank, local_rank, world):
     P, N = WORKLOAD["num_players"], args.envs
     K, W = args.steps, args.warmup
 
-    def make_batch():
+    def make_batch(j=0):
+        # global env ids: every batch of every rank has its own contiguous slice
         return GameBatch(N, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
-                         seed=WORKLOAD["seed"], env_id_base=rank * N, auto_reset=True, device=local_rank)
+                         seed=WORKLOAD["seed"], env_id_base=(rank * RESIDENT_BATCHES + j) * N, auto_reset=True,
+                         device=local_rank)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    g = make_batch()
-    g.reset()
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    for t in range(W):
-        g.step_random(t)
-    torch.cuda.synchronize()
-    g.stats_reset()
+    batches = [make_batch(j) for j in range(RESIDENT_BATCHES)]
+    for g in batches:
+        g.reset()
+    t_idx = 0  # step index of the device-side random agents (per batch it only has to be distinct per step)
 
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    def step_next():
+        nonlocal t_idx
+        batches[t_idx % RESIDENT_BATCHES].step_random(t_idx)  # ONE launch: fused sampler + Game.step on N envs
+        t_idx += 1
+
+    for _ in range(max(W, RESIDENT_BATCHES)):
+        step_next()
+    torch.cuda.synchronize()
+    for g in batches:
+        g.stats_reset()
+
+    main = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(RESIDENT_BATCHES)]
+
+    def run_steps(n, overlapped):
+        """n steps round-robin over the resident batches; overlapped: one stream per batch, joined at the end."""
+        nonlocal t_idx
+        if overlapped:
+            for st in streams:
+                st.wait_stream(main)
+        for _ in range(n):
+            j = t_idx % RESIDENT_BATCHES
+            if overlapped:
+                with torch.cuda.stream(streams[j]):
+                    batches[j].step_random(t_idx)
+            else:
+                batches[j].step_random(t_idx)
+            t_idx += 1
+        if overlapped:
+            for st in streams:
+                main.wait_stream(st)
+
+    run_steps(2 * RESIDENT_BATCHES, True)
+    torch.cuda.synchronize()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     barrier()
     wall0 = time.perf_counter()
-    for i in range(K):
-        flush.zero_()                 # evict the 86 MB state from L2 (untimed)
-        starts[i].record()
-        g.step_random(W + i)          # ONE launch: fused sampler + Game.step on all N envs
-        stops[i].record()
+    e_start.record()
+    run_steps(K, True)
+    e_stop.record()
     barrier()
     wall = time.perf_counter() - wall0
     clock_info = clocks.stop() if rank == 0 else None
-    per_step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    dev_ms = sum(per_step_ms)
-
-    # ---- L2-resident variant (no flush), reported as context only
-    barrier()
+    dev_ms = e_start.elapsed_time(e_stop)
+    # the same K steps on ONE stream: every launch alone on the GPU (the kernel's own duration)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
-    for i in range(K):
-        g.step_random(W + K + i)
+    run_steps(K, False)
     e1.record()
     torch.cuda.synchronize()
-    resident_ms = e0.elapsed_time(e1)
-    stats = g.stats()
+    isolated_ms = e0.elapsed_time(e1) / K
+    stats = batches[0].stats()
+    for g in batches[1:]:
+        sj = g.stats()
+        for k in ("steps", "hands", "showdowns", "games", "invalid", "poisoned"):
+            stats[k] += sj[k]
+        stats["payoff_sum"] = [a + b for a, b in zip(stats["payoff_sum"], sj["payoff_sum"])]
 
-    # ---- end to end through the public API with HOST buffers: per step H2D actions, step, D2H flags+valid
-    E = min(K, 128)
-    rec = make_batch()
-    rec.reset()
-    host_actions = torch.empty((E, N), dtype=torch.int32).pin_memory()
-    for t in range(E):
-        rec.step_random(t, record_actions=True)
-        host_actions[t].copy_(rec.actions_taken)
+    # ---- for reference: one batch, L2 flushed by a 256 MB memset before every step (each step timed on its own)
+    g = batches[0]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    KF = min(K, 64)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
+    barrier()
+    for i in range(KF):
+        flush.zero_()
+        starts[i].record()
+        g.step_random(t_idx + i)
+        stops[i].record()
     torch.cuda.synchronize()
-    del rec
-    run = make_batch()
-    run.reset()
-    dev_actions = torch.empty(N, dtype=torch.int32, device=dev)
-    host_flags = torch.empty(N, dtype=torch.uint8).pin_memory()
-    host_valid = torch.empty(N, dtype=torch.uint8).pin_memory()
+    flushed_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / KF
+    # ---- and the same batch back to back without any flush (its state stays in the 126 MB L2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(KF):
+        g.step_random(t_idx + KF + i)
+    e1.record()
+    torch.cuda.synchronize()
+    resident_ms = e0.elapsed_time(e1) / KF
+    del flush
+
+    # ---- end to end through the public API with HOST buffers.  Every step: H2D copy of that step's actions from
+    # pinned host memory, GameBatch.step, D2H copy of its flags and valid masks.  As in the device-resident leg, the
+    # three independent resident batches take turns, each on its own stream, so one batch's copies overlap another
+    # batch's step (a caller that keeps several env batches in flight does exactly this); the actions are a
+    # recording of the device-side random agents, so every one of them is valid for the state it meets.
+    R = max(1, min(K, 126) // RESIDENT_BATCHES)  # rounds; E = R * RESIDENT_BATCHES steps
+    E = R * RESIDENT_BATCHES
+    host_actions, runs = [], []
+    for j in range(RESIDENT_BATCHES):
+        rec = make_batch(j)
+        rec.reset()
+        ha = torch.empty((R, N), dtype=torch.int32).pin_memory()
+        for r in range(R):
+            rec.step_random(r, record_actions=True)
+            ha[r].copy_(rec.actions_taken)
+        torch.cuda.synchronize()
+        del rec
+        host_actions.append(ha)
+        run = make_batch(j)
+        run.reset()
+        runs.append(run)
+    dev_actions = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(RESIDENT_BATCHES)]
+    host_flags = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(RESIDENT_BATCHES)]
+    host_valid = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(RESIDENT_BATCHES)]
     barrier()
     t0 = time.perf_counter()
-    for t in range(E):
-        dev_actions.copy_(host_actions[t], non_blocking=True)
-        flags, valid = run.step(dev_actions)
-        host_flags.copy_(flags, non_blocking=True)
-        host_valid.copy_(valid, non_blocking=True)
-        torch.cuda.synchronize()
+    for st in streams:
+        st.wait_stream(main)
+    for r in range(R):
+        for j in range(RESIDENT_BATCHES):
+            with torch.cuda.stream(streams[j]):
+                dev_actions[j].copy_(host_actions[j][r], non_blocking=True)
+                flags, valid = runs[j].step(dev_actions[j])
+                host_flags[j].copy_(flags, non_blocking=True)
+                host_valid[j].copy_(valid, non_blocking=True)
+    for st in streams:
+        st.synchronize()
     e2e_s = time.perf_counter() - t0
-    bad = int(((host_flags & (nat.F_INVALID | nat.F_POISONED)) != 0).sum())
-    assert bad == 0, f"e2e replay produced {bad} rejected actions"
-    del run
+    rejected = sum(run.stats()["invalid"] for run in runs)
+    assert rejected == 0, f"e2e replay produced {rejected} rejected actions"
+    del runs
 
     # ---- 7-card hand evals/s on random hands resident in HBM (12 B per eval: 8 in, 4 out)
     n_hands = 1 << 27
@@ -296,13 +376,13 @@ def run_ours(args, rank, local_rank, world):
     del masks, out
 
     # ---- max over ranks; NCCL reduction of the statistics vector (the only collective)
-    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms], dtype=torch.float64, device=dev)
+    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, flushed_ms, isolated_ms], dtype=torch.float64, device=dev)
     svec = torch.tensor([stats["steps"], stats["hands"], stats["showdowns"], stats["games"], stats["invalid"],
                          stats["poisoned"]] + stats["payoff_sum"], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(svec, op=dist.ReduceOp.SUM)
-    dev_ms, resident_ms, e2e_s, eval_ms = vec.tolist()
+    dev_ms, resident_ms, e2e_s, eval_ms, flushed_ms, isolated_ms = vec.tolist()
     if rank != 0:
         return
 
@@ -319,14 +399,21 @@ def run_ours(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "kernel": "pkb::step_tile_kernel<2,true>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("step_kernel_p2"),
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_step(P),
-                     "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src},
+                     "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
+                     "avg_launch_note": "timed region / launches; the launches of the three resident batches run on three streams and overlap",
+                     "isolated_launch_us": isolated_ms * 1e3, "isolated_achieved": bytes_per_launch / (isolated_ms / 1e3) / 1e9,
+                     "isolated_frac": bytes_per_launch / (isolated_ms / 1e3) / 1e9 / peak, "peak_source": peak_src},
         "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N,
                 "d2h_bytes_per_step": 2 * N, "steps": E,
-                "path": "GameBatch.step(actions from pinned host) -> pkb_step -> flags+valid to pinned host, sync per step"},
+                "path": "per step: actions H2D from pinned host -> GameBatch.step -> pkb_step -> flags+valid D2H to pinned host; "
+                        "the three resident batches take turns on three streams, host synchronises at the end"},
         "gpu_launches": K,  # one persistent step_tile_kernel launch per step
         "clocks": clock_info,
-        "l2_resident": {"value": N * world * K / (resident_ms / 1e3), "unit": "env-steps/s",
-                        "note": "same K steps back to back without the L2 flush (state stays in the 126 MB L2)"},
+        "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",
+                        "note": "one batch stepped back to back: its 86 MB of state stays in the 126 MB L2"},
+        "flushed_by_memset": {"value": N * world / (flushed_ms / 1e3), "unit": "env-steps/s", "us_per_step": flushed_ms * 1e3,
+                              "note": "one batch, 256 MB memset before every step, each step timed on its own: the step "
+                                      "also pays for writing the memset's dirty lines out of L2"},
         "hand_evals": {"metric": "hand_evals_per_sec", "value": eval_rate, "unit": "7-card evals/s", "hands": n_hands,
                        "roofline": {"bound": "hbm", "kernel": "pkb::eval_masks_kernel", "achieved": 12 * eval_rate / world / 1e9,
                                     "peak": peak, "unit": "GB/s", "frac": 12 * eval_rate / world / 1e9 / peak,
