@@ -115,6 +115,13 @@ class ClockSampler:
 # not exist on the GPU box; see DESIGN.md "CPU baseline")
 # ------------------------------------------------------------------------------------------------
 
+def use_all_host_threads(ora):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU comparator is meant to use every host core."""
+    cores = os.cpu_count() or 1
+    ora.lib().ora_batch_set_threads(cores)
+    return cores
+
+
 def cpu_rate_probe(ora, P):
     b = ora.OracleBatch(1 << 14, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
                         seed=WORKLOAD["seed"], auto_reset=True)
@@ -129,7 +136,7 @@ def cpu_baseline(target_seconds=12.0) -> dict:
     """Oracle port timed on a bounded sample of the same workload (rank 0, N=1 only)."""
     from oracle import pyoracle as ora
     P = WORKLOAD["num_players"]
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads(ora)
     rate = cpu_rate_probe(ora, P)
     envs = 1 << 16
     steps = max(16, min(4096, int(rate * target_seconds / envs)))
@@ -151,7 +158,7 @@ def run_reference(args, rank, world):
         return
     from oracle import pyoracle as ora
     P = WORKLOAD["num_players"]
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads(ora)
     rate = cpu_rate_probe(ora, P)
     total_steps = args.steps + args.warmup
     # bounded sample: as many envs (<= the full 2^20) as keep the whole run near one minute
