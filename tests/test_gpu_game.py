@@ -239,6 +239,35 @@ def test_full_size_heads_up_sampled_parity(torch_cuda, ora):
     assert (total <= 200.0 + 1e-9).all()
 
 
+def test_full_size_nine_player_side_pot_heavy_sampled_parity(torch_cuda, ora):
+    """BASELINE config 4 at its full size (2^22 envs, nine players, unequal stacks 20..180, action mix that is 45 %
+    all-in so that multi-layer side pots are common): T fused weighted-random steps, then env windows at both ends and
+    in the middle compared bit-exactly with the oracle (n >= 8 np.sum order, side-pot layers), plus whole-batch
+    properties."""
+    from pokerl_b200 import GameBatch
+    N, P, T = 1 << 22, 9, 40
+    start = [20 * (i + 1) for i in range(P)]
+    weights = [10, 30, 30, 5, 5, 5, 45]  # FOLD .10, CHECK/CALL .30, RAISE_x .05 each, ALL_IN .45 (SURVEY 8d)
+    g = GameBatch(N, P, start, 2, 1, seed=1, auto_reset=True)
+    g.reset()
+    for t in range(T):
+        g.step_random(t, weights)
+    e = g.export()
+    for base in (0, 2_000_000, N - 1024):
+        W = 1024
+        o = ora.OracleBatch(W, P, start, 2, 1, seed=1, env_id_base=base, auto_reset=True)
+        o.reset()
+        o.run_random(0, T, weights)
+        win = {k: np.asarray(v)[..., base:base + W] for k, v in e.items()}
+        assert_state_equal(win, o.export(), ctx=f"window {base}")
+    st = g.stats()
+    assert st["steps"] == N * T and st["invalid"] == 0 and st["showdowns"] > N
+    assert (e["states"] <= 4).all() and (e["turn"] <= 3).all() and (e["active"] < P).all()
+    # chips are only ever destroyed (the reference's skipped-street quirk), never created
+    total = e["credits"].sum(axis=0) + e["bets"].sum(axis=0)
+    assert (total <= sum(start) + 1e-9).all()
+
+
 def test_scalar_facade_random_game(torch_cuda, ora):
     """examples/random_game.py shape: Game(num_players=4, start_credits=1000, big_blind=40, small_blind=20) played to
     the end through the reference-style scalar API, mirrored step by step by the oracle."""
