@@ -50,6 +50,15 @@ PKB_HD int topbit32(uint32_t x)
     return 31 - __builtin_clz(x);
 #endif
 }
+// 1-based index of the lowest set bit, 0 for x == 0
+PKB_HD int ffs32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
 PKB_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {
 #ifdef __CUDA_ARCH__

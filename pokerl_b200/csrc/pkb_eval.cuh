@@ -178,6 +178,76 @@ PKB_HD uint32_t eval_mask52_tbl(uint64_t m, const uint32_t* __restrict__ tbl)
     return m == 0 ? PACKED_NONE : r;
 }
 
+// ---- select form of eval_mask52 (the step kernels) -----------------------------------------------------
+//
+// eval_mask52 returns early from whichever category it finds first, so a warp that ranks 32 different
+// hands executes every category's code one after the other.  This form computes the same value with
+// selects only (the structure of eval_mask52_tbl, with the table look-ups replaced by clz / popc), so all
+// lanes run the same ~150 instructions and several hands of one thread can be interleaved.  It is
+// verified equal to eval_mask52 on all C(52,k) hands, k = 1..7 (tests/test_host_logic.py, hostcheck).
+PKB_HD uint32_t top_rank(uint32_t x) { return x ? (uint32_t)topbit32(x) + 1u : 0u; }  // highest rank of a set as a nibble, 0: empty
+PKB_HD uint32_t drop_top(uint32_t x) { return x ? x ^ (1u << topbit32(x)) : 0u; }
+
+// append the k highest ranks of x as nibbles below v (pack_top without data-dependent branches)
+PKB_HD uint32_t pack_top_sel(uint32_t x, int k, uint32_t v)
+{
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const bool take = i < k && x != 0;
+        const int h = topbit32(x | 1u);
+        v = take ? (v << 4) | (uint32_t)(h + 1) : v;
+        x = take ? x ^ (1u << h) : x;
+    }
+    return v;
+}
+
+PKB_HD uint32_t eval_mask52_sel(uint64_t m)
+{
+    const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
+    const uint32_t any = s0 | s1 | s2 | s3;
+
+    // suit X (flush suit, else the lowest-numbered suit present) and its lowest maximal run
+    const bool f0 = popc32(s0) >= 5, f1 = popc32(s1) >= 5, f2 = popc32(s2) >= 5, f3 = popc32(s3) >= 5;
+    const uint32_t fl = f0 ? s0 : f1 ? s1 : f2 ? s2 : f3 ? s3 : 0u;
+    const uint32_t sx = fl ? fl : s0 ? s0 : s1 ? s1 : s2 ? s2 : s3;
+    const uint32_t run = sx & ~(sx + (sx & (0u - sx)));
+    const uint32_t st_hi = top_rank(any & (any << 1) & (any << 2) & (any << 3) & (any << 4));
+
+    // rank multiplicities, bit-sliced
+    const uint32_t a01 = s0 & s1, x01 = s0 ^ s1, a23 = s2 & s3, x23 = s2 ^ s3;
+    const uint32_t quad = a01 & a23;
+    const uint32_t trip = (a01 & x23) | (x01 & a23);
+    const uint32_t pair = (a01 & ~(s2 | s3)) | (a23 & ~(s0 | s1)) | (x01 & x23);
+    const uint32_t trip_rest = drop_top(trip), pair_rest = drop_top(pair);
+    const uint32_t q = top_rank(quad), t = top_rank(trip), t2 = top_rank(trip_rest), p1 = top_rank(pair), p2 = top_rank(pair_rest);
+
+    const bool c_quad = quad != 0;
+    const bool c_full = !c_quad && trip != 0 && (trip_rest != 0 || pair != 0);
+    const bool c_flush = !c_quad && !c_full && fl != 0;
+    const bool c_straight = !c_quad && !c_full && !c_flush && st_hi != 0;
+    const bool c_tris = !c_quad && !c_full && !c_flush && !c_straight && trip != 0;
+    const bool c_two = !c_quad && !c_full && !c_flush && !c_straight && !c_tris && pair_rest != 0;
+    const bool c_pair = !c_quad && !c_full && !c_flush && !c_straight && !c_tris && !c_two && pair != 0;
+    // the ranks that lead the kicker word, the set the remaining kickers come from and how many of them count
+    const uint32_t lead_set = c_quad ? quad ^ drop_top(quad) : c_tris ? trip ^ trip_rest
+                              : c_two ? pair ^ drop_top(pair_rest) : c_pair ? pair ^ pair_rest : 0u;
+    const uint32_t lead = c_quad ? q : c_tris ? t : c_two ? p1 << 4 | p2 : c_pair ? p1 : 0u;
+    const int k = c_quad ? 1 : c_tris ? 2 : c_two ? 1 : c_pair ? 3 : 5;
+    const uint32_t cat = c_flush ? HR_FLUSH : c_quad ? HR_POKER : c_tris ? HR_TRIS : c_two ? HR_TWO_PAIR : c_pair ? HR_PAIR : HR_HIGH;
+    uint32_t r = cat << 20 | pack_top_sel(c_flush ? fl : any & ~lead_set, k, c_flush ? 0u : lead);  // judger.py:91, 94, 96-99
+    r = c_full ? (HR_FULL << 20) | t << 4 | (trip_rest ? t2 : p1) : r;                                    // :92-93
+    r = c_straight ? (HR_STRAIGHT << 20) | st_hi : r;                                                     // :95
+    // the straight-flush tracker and the two wheel special cases come first (judger.py:83-90)
+    const bool run_is_wheel_low = run == 0xFu;
+    r = popc32(run) >= 5 ? (HR_STRAIGHT_FLUSH << 20) | top_rank(run) : r;
+    const bool wheel = !run_is_wheel_low && st_hi == 0 && (any & 0x1000u) && (any & ~(any + (any & (0u - any)))) == 0xFu;
+    r = wheel ? (HR_STRAIGHT << 20) | 4u : r;
+    r = run_is_wheel_low && (sx & 0x1000u) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;
+    return m == 0 ? PACKED_NONE : r;
+}
+// out-of-line copy for callers that rank many seats in a rolled loop
+PKB_HD_CALL uint32_t eval_mask52_sel_call(uint64_t m) { return eval_mask52_sel(m); }
+
 // ---- list form (duplicates allowed): the two-sorted-copies scan of judger.py:38-99 ----------------
 
 PKB_HD int cv_rank(uint32_t v) { const int r = (int)(v & 0xfu); return r ? r : 13; }

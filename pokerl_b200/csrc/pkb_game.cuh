@@ -33,6 +33,12 @@ struct GameConst {
     int32_t dealer;
     int32_t auto_reset;
     int32_t track_stats;
+    // The state right after Game.reset() (game.py:397-412) -- a function of the configuration only, worked out once on the
+    // host (fill_fresh_state) so that the auto-reset of a finished game is a copy, not a second setup_hand.
+    // credits = start_credits, bets = 0, hand = 1.
+    double fresh_pending[MAX_PLAYERS];
+    double fresh_min_raise;
+    uint32_t fresh_meta, fresh_active, fresh_called, fresh_allin;
 };
 
 template <int LD>
@@ -45,18 +51,18 @@ struct View {
     uint32_t* meta;  // packed indices   [ld]
     uint32_t* hand;  // hand counter     [ld]
     size_t ld_rt;
-    PKB_D size_t ld() const { return LD ? (size_t)LD : ld_rt; }
+    PKB_HDM size_t ld() const { return LD ? (size_t)LD : ld_rt; }
 };
 
 // turn | dealer<<3 | small_blind_idx<<8 | big_blind_idx<<13 | active_player<<18
 struct Meta {
     int turn, dealer, sb, bb, act;
 };
-PKB_D Meta unpack_meta(uint32_t w)
+PKB_HD Meta unpack_meta(uint32_t w)
 {
     return Meta{(int)(w & 7u), (int)(w >> 3 & 31u), (int)(w >> 8 & 31u), (int)(w >> 13 & 31u), (int)(w >> 18 & 31u)};
 }
-PKB_D uint32_t pack_meta(const Meta& m)
+PKB_HD uint32_t pack_meta(const Meta& m)
 {
     return (uint32_t)m.turn | (uint32_t)m.dealer << 3 | (uint32_t)m.sb << 8 | (uint32_t)m.bb << 13 | (uint32_t)m.act << 18;
 }
@@ -67,7 +73,7 @@ struct Seats {
 };
 
 template <int P>
-PKB_D constexpr uint32_t all_seats() { return (1u << P) - 1u; }
+PKB_HD constexpr uint32_t all_seats() { return (1u << P) - 1u; }
 
 template <int P, class V>
 PKB_D Seats load_seats(const V& v, size_t s)
@@ -94,7 +100,7 @@ PKB_D void store_seats(V& v, size_t s, const Seats& x)
 }
 
 // player_states[p] = state
-PKB_D void set_state(Seats& x, int p, int state)
+PKB_HD void set_state(Seats& x, int p, int state)
 {
     const uint32_t bit = 1u << p, keep = ~bit;
     x.active = (x.active & keep) | (state == ST_ACTIVE ? bit : 0u);
@@ -104,10 +110,10 @@ PKB_D void set_state(Seats& x, int p, int state)
 }
 
 // first set bit of `mask` at or after seat `idx` in cyclic order; mask != 0, idx < 32
-PKB_D int first_from(uint32_t mask, int idx)
+PKB_HD int first_from(uint32_t mask, int idx)
 {
     const uint32_t hi = mask >> idx << idx;
-    return __ffs((int)(hi ? hi : mask)) - 1;
+    return ffs32(hi ? hi : mask) - 1;
 }
 
 // numpy float64 add.reduce order (pairwise_sum): n < 8 left to right from 0.0; n >= 8 eight lanes,
@@ -139,7 +145,7 @@ PKB_D double sum_plane(const V& v, const double* plane, size_t s)
 
 // Game.get_first_playing, game.py:334-337; idx in [0, 2P)
 template <int P>
-PKB_D int first_playing(const Seats& x, int idx)
+PKB_HD int first_playing(const Seats& x, int idx)
 {
     if (idx >= P) idx -= P;
     const uint32_t alive = all_seats<P>() & ~x.broken;
@@ -191,7 +197,7 @@ PKB_D uint32_t valid_mask(const V& v, size_t s, int player)
 // Game.setup_hand, game.py:414-451.  The deck is not materialised: hand `hand` of this episode is
 // a pure function of (seed, env, episode, hand) and is regenerated where it is needed.
 template <int P, class V>
-PKB_D void setup_hand(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
+PKB_HD void setup_hand(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
 {
     const size_t ld = v.ld();
     v.hand[s] += 1;
@@ -219,7 +225,7 @@ PKB_D void setup_hand(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
 
 // Game.reset, game.py:397-412 (the episode counter is bumped by the caller)
 template <int P, class V>
-PKB_D void reset_env(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
+PKB_HD void reset_env(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
 {
     const size_t ld = v.ld();
     m.dealer = gc.dealer;  // :403
@@ -229,6 +235,25 @@ PKB_D void reset_env(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
     for (int p = 0; p < P; ++p) v.cr[p * ld + s] = gc.start_credits[p];  // :408
     x = Seats{all_seats<P>(), 0, 0, 0};                                  // :409
     setup_hand<P>(v, s, x, m, gc);
+}
+
+// host side: fills the fresh_* fields of gc by running Game.reset on one scratch table
+template <int P>
+inline void fill_fresh_state(GameConst& gc)
+{
+    double cr[P], bt[P], pd[P], mr[1] = {0.0};
+    uint8_t st[P];
+    uint32_t meta[1] = {0}, hand[1] = {0};
+    View<0> v{cr, bt, pd, mr, st, meta, hand, 1};
+    Seats x{0, 0, 0, 0};
+    Meta m = unpack_meta(0);
+    reset_env<P>(v, 0, x, m, gc);
+    for (int p = 0; p < MAX_PLAYERS; ++p) gc.fresh_pending[p] = p < P ? pd[p] : 0.0;
+    gc.fresh_min_raise = mr[0];
+    gc.fresh_meta = pack_meta(m);
+    gc.fresh_active = x.active;
+    gc.fresh_called = x.called;
+    gc.fresh_allin = x.allin;
 }
 
 // game.py:457-461 and 554-558
@@ -403,7 +428,7 @@ PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c)
         return false;
     }
     if (n == 1) {  // :475-482
-        const int first = __ffs((int)contenders) - 1;
+        const int first = ffs32(contenders) - 1;
         const double pot = sum_plane<P>(v, v.bt, s);
         v.pd[first * ld + s] = pot;
         v.cr[first * ld + s] += pot;
@@ -421,7 +446,17 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
     uint32_t rk[P];
     double b[P], pay[P];
     uint32_t todo = x.called | x.allin;  // :488, :496 seats that show their cards
-    {  // :488-489 eval_hand(board + hole) for CALLED / ALL_IN seats, NONE for the others
+    // :488-489 eval_hand(board + hole) for CALLED / ALL_IN seats, NONE for the others
+    if constexpr (5 + 2 * P <= 13) {  // small tables: interleaved Philox blocks, sorted draw chain, select-form ranks
+        uint32_t id[5 + 2 * P];
+        deal_ids<5 + 2 * P>(seed, env_id, episode, v.hand[s], id);
+        const uint64_t board = 1ull << id[0] | 1ull << id[1] | 1ull << id[2] | 1ull << id[3] | 1ull << id[4];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const uint32_t r = eval_mask52_sel(board | 1ull << id[5 + 2 * p] | 1ull << id[6 + 2 * p]);
+            rk[p] = (todo >> p & 1u) ? r : PACKED_NONE;
+        }
+    } else {
         Dealer d(seed, env_id, episode, v.hand[s]);
         uint64_t board = 0;
 #pragma unroll
@@ -429,10 +464,13 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const uint64_t hole = (1ull << d.next()) | (1ull << d.next());
-            rk[p] = (todo >> p & 1u) ? eval_mask52(board | hole) : PACKED_NONE;
-            b[p] = v.bt[p * ld + s];  // :485 working copy
-            pay[p] = 0.0;
+            rk[p] = (todo >> p & 1u) ? eval_mask52_sel_call(board | hole) : PACKED_NONE;
         }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        b[p] = v.bt[p * ld + s];  // :485 working copy
+        pay[p] = 0.0;
     }
     int n = c.npw;
     while (todo) {  // :496-498 seats by ascending bet, ties by seat (np.argsort, numpy 1.18.4 order)
@@ -511,21 +549,20 @@ PKB_D bool end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* pa
     }
     // :539 setup_hand runs even when the game is over -- and it can bring BROKEN seats with a negative
     // stack back as ALL_IN, so game_over is read after it, as the callers do
-    // (:565, :619).  A second trip through the same code is Game.reset's setup_hand (:412).
-    bool over = false, reset_now = false;
-#pragma unroll 1
-    for (int trip = 0; trip < 2; ++trip) {
-        setup_hand<P>(v, s, x, m, gc);
-        if (trip == 1) break;
-        over = game_over<P>(x);
-        reset_now = over && gc.auto_reset && !c.poisoned;
-        if (!reset_now) break;
-        m.dealer = gc.dealer;  // Game.reset, :403-409
-        m.act = 0;
-        v.hand[s] = 0;
+    // (:565, :619).
+    setup_hand<P>(v, s, x, m, gc);
+    const bool over = game_over<P>(x);
+    const bool reset_now = over && gc.auto_reset && !c.poisoned;
+    if (reset_now) {  // Game.reset (game.py:397-412): its outcome depends on the configuration only
+        v.hand[s] = 1;
 #pragma unroll
-        for (int p = 0; p < P; ++p) v.cr[p * ld + s] = gc.start_credits[p];
-        x = Seats{all_seats<P>(), 0, 0, 0};
+        for (int p = 0; p < P; ++p) {
+            v.cr[p * ld + s] = gc.start_credits[p];
+            v.pd[p * ld + s] = gc.fresh_pending[p];
+        }
+        v.mr[s] = gc.fresh_min_raise;
+        m = unpack_meta(gc.fresh_meta);
+        x = Seats{gc.fresh_active, gc.fresh_called, gc.fresh_allin, 0};
     }
     const int flag = over ? (int)F_GAME_OVER : 0;
     if (c.cont) {  // next_turn: `return self.game_over, True, True`, then the scan goes on (:609-611)

@@ -9,6 +9,7 @@
 //   sample_kernel    K5          RandomAgent over the valid mask
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -36,7 +37,15 @@ struct DevState {
 
 enum : int { STAT_STEPS = 0, STAT_HANDS, STAT_SHOWDOWNS, STAT_GAMES, STAT_INVALID, STAT_POISONED, STAT_COUNT };
 
+// TMA descriptors of the three plane groups of a handle (2-D: [rows][stride]), box = [rows][warp tile]
+struct alignas(64) TileMaps {
+    CUtensorMap f64;  // credits, bets, pending_bets ([P] rows each) and minimum_raise_value: 3P + 1 rows of f64
+    CUtensorMap u32;  // meta, hand, episode
+    CUtensorMap u8;   // player_states: P rows
+};
+
 struct StepArgs {
+    TileMaps maps;
     DevState d;
     GameConst gc;
     const int32_t* actions;
@@ -100,6 +109,7 @@ PKB_D View<0> global_view(const DevState& d)
 template <int P>
 struct Tile {
     static constexpr int T = tile_envs<P>();
+    static constexpr int NP = P;
     static constexpr int NBUF = 2;
     static constexpr int ROWS = 4 * P + 3;       // rows stored back: 3P f64 seat rows, mr, meta, hand, P state rows
     static constexpr int LOAD_ROWS = ROWS + 1;   // + the episode counters (read-only in the tile: the deal replay is keyed by them)
@@ -132,17 +142,26 @@ PKB_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-PKB_D void mbar_wait(uint32_t bar, uint32_t parity)
+PKB_D bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");  // suspend-time hint (ns): do not spin on issue slots
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): do not spin on issue slots
+        : "memory");
+    return ok != 0;
+}
+// Watchdog: a tile load that has not landed after 2^18 polls (milliseconds at least) never will; abort the
+// launch with an error instead of hanging the device.
+PKB_D void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls)
+        if (polls > (1u << 18)) __trap();
 }
 // TMA 1-D bulk copies (SASS: UBLKCP); sizes and addresses are multiples of 16 bytes
 PKB_D void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
@@ -156,17 +175,29 @@ PKB_D void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes)
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
                  : "memory");
 }
+// TMA 2-D tiled copies (SASS: UTMALDG / UTMASTG): box [rows][tile envs] <-> dense shared-memory rows
+PKB_D void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+PKB_D void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src_smem)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(src_smem)
+                 : "memory");
+}
 PKB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 PKB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 PKB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // row r of a tile: where it lives in HBM (for the tile that starts at env `base`) and inside a tile buffer
-template <int P>
+template <class L>
 PKB_D void tile_row(const DevState& d, size_t base, int r, char*& gptr, uint32_t& soff, uint32_t& bytes)
 {
-    using L = Tile<P>;
-    constexpr int T = L::T;
+    constexpr int T = L::T, P = L::NP;
     if (r < 3 * P) {
         const int plane = r / P, seat = r - plane * P;
         double* g = plane == 0 ? d.cr : plane == 1 ? d.bt : d.pd;
@@ -197,10 +228,9 @@ PKB_D void tile_row(const DevState& d, size_t base, int r, char*& gptr, uint32_t
     }
 }
 
-template <int P>
-PKB_D View<Tile<P>::T> tile_view(unsigned char* smem)
+template <class L>
+PKB_D View<L::T> tile_view(unsigned char* smem)
 {
-    using L = Tile<P>;
     View<L::T> v;
     v.cr = reinterpret_cast<double*>(smem + L::OFF_CR);
     v.bt = reinterpret_cast<double*>(smem + L::OFF_BT);
@@ -312,7 +342,7 @@ __device__ __noinline__ void run_further_hands(unsigned char* buf, uint32_t* ctl
                                                const StepArgs& a)
 {
     using L = Tile<P>;
-    View<L::T> v = tile_view<P>(buf);
+    View<L::T> v = tile_view<L>(buf);
     const DevState& d = a.d;
     Seats x = load_seats<P>(v, s);
     Ctl c = unpack_ctl(ctl[s]);
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
         if (tid < L::LOAD_ROWS) {
             char* g;
             uint32_t soff, bytes;
-            tile_row<P>(d, (size_t)tile * T, tid, g, soff, bytes);
+            tile_row<L>(d, (size_t)tile * T, tid, g, soff, bytes);
             bulk_wait_read();  // this row's last store has left shared memory
             mbar_arrive_expect_tx(smem_base + 8 * b, bytes);
             bulk_load(smem_base + (uint32_t)(L::HEADER + b * L::BUF_BYTES) + soff, g, bytes, smem_base + 8 * b);
@@ -397,7 +427,7 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
     for (uint32_t it = 0; tile < a.num_tiles; ++it) {
         const int b = (int)(it % NBUF);
         unsigned char* buf = smem + L::HEADER + b * L::BUF_BYTES;
-        View<T> v = tile_view<P>(buf);
+        View<T> v = tile_view<L>(buf);
         const uint32_t* ep = reinterpret_cast<const uint32_t*>(buf + L::OFF_EP);
         const size_t base = (size_t)tile * T;
         if (tid == 0) next_tile[(it + 1) & 1] = atomicAdd(&d.sched[0], 1u);  // read by everyone after pass A's barrier
@@ -522,7 +552,7 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
         for (int r = 0; r < L::ROWS; ++r) {  // experiment: plain 128-bit coalesced stores instead of TMA
             char* g;
             uint32_t soff, bytes;
-            tile_row<P>(d, base, r, g, soff, bytes);
+            tile_row<L>(d, base, r, g, soff, bytes);
             for (uint32_t o = tid * 16; o < bytes; o += STEP_THREADS * 16)
                 *reinterpret_cast<uint4*>(g + o) = *reinterpret_cast<const uint4*>(buf + soff + o);
         }
@@ -530,7 +560,7 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
         if (tid < L::ROWS) {
             char* g;
             uint32_t soff, bytes;
-            tile_row<P>(d, base, tid, g, soff, bytes);
+            tile_row<L>(d, base, tid, g, soff, bytes);
             bulk_store(g, smem_base + (uint32_t)(L::HEADER + b * L::BUF_BYTES) + soff, bytes);
             bulk_commit();
         }
@@ -566,6 +596,260 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
         atomicMax(&g_span[2], gt1);
     }
 #endif
+    if (a.gc.track_stats) reduce_stats<P>(d, tl);
+}
+
+// --------------------------------------------------------------------------------------------
+// Game.step on every env, warp-tile form (the default): the same three passes, but a tile belongs to
+// ONE WARP.  A warp pulls the plane rows of its WT consecutive envs into its own shared-memory
+// buffer (TMA bulk copies on the warp's own mbarrier), runs pass A over WT/32 slots per lane, builds
+// the two work lists with ballots (no atomics), runs passes C and D on them, and pushes the rows back.
+// There is no block barrier anywhere in the loop, so a warp whose tile holds many showdowns (or a slot
+// that plays several hands in one step) delays nobody else; the 20-odd resident warps per SM cover
+// each other's load latency and dependent-instruction stalls.
+// --------------------------------------------------------------------------------------------
+#ifndef PKB_WT_SMALL
+#define PKB_WT_SMALL 128  // envs per warp tile, P <= 3
+#endif
+#ifndef PKB_WT_MID
+#define PKB_WT_MID 128    // P == 4
+#endif
+#ifndef PKB_WT_LARGE
+#define PKB_WT_LARGE 64   // P >= 5
+#endif
+#ifndef PKB_WT_WARPS
+#define PKB_WT_WARPS 4    // warps per block (they only share the block's statistics reduction)
+#endif
+static_assert(STRIDE_ALIGN % PKB_WT_SMALL == 0 && STRIDE_ALIGN % PKB_WT_MID == 0 && STRIDE_ALIGN % PKB_WT_LARGE == 0, "warp tiles must divide the plane stride");
+
+template <int P>
+__host__ __device__ constexpr int wt_envs()
+{
+    return P <= 3 ? PKB_WT_SMALL : P == 4 ? PKB_WT_MID : PKB_WT_LARGE;
+}
+
+template <int P>
+struct WarpTile {
+    static constexpr int T = wt_envs<P>();
+    static constexpr int NP = P;
+    // one buffer = three dense row groups, each the box of one TMA descriptor (same row order as the HBM arena)
+    static constexpr int F64_ROWS = 3 * P + 1;  // credits[P], bets[P], pending[P], minimum_raise
+    static constexpr int U32_ROWS = 3;          // meta, hand, episode
+    static constexpr size_t OFF_CR = 0;
+    static constexpr size_t OFF_BT = OFF_CR + (size_t)P * T * 8;
+    static constexpr size_t OFF_PD = OFF_BT + (size_t)P * T * 8;
+    static constexpr size_t OFF_MR = OFF_PD + (size_t)P * T * 8;
+    static constexpr size_t OFF_META = OFF_MR + (size_t)T * 8;
+    static constexpr size_t OFF_HAND = OFF_META + (size_t)T * 4;
+    static constexpr size_t OFF_EP = OFF_HAND + (size_t)T * 4;
+    static constexpr size_t OFF_ST = OFF_EP + (size_t)T * 4;
+    static constexpr size_t BUF_BYTES = OFF_ST + (size_t)P * T;  // = bytes of the three boxes
+    // per warp: buffer | list E (u32: slot | control word << 8) | list S (u8 slot); the warps' mbarriers sit in the block header
+    static constexpr size_t OFF_LIST_E = (BUF_BYTES + 15) / 16 * 16;
+    static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 4;
+    static constexpr size_t WARP_BYTES = (OFF_LIST_S + (size_t)T + 127) / 128 * 128;
+    static constexpr size_t HEADER = 128;
+    static constexpr size_t BYTES = HEADER + WARP_BYTES * PKB_WT_WARPS;
+    static constexpr int THREADS = 32 * PKB_WT_WARPS;
+    // resident blocks per SM that 227 KB of shared memory (1 KB reserved per block) and 64 K registers at >= 64 per thread allow
+    static constexpr int BY_SMEM = (int)((227 * 1024) / (BYTES + 1024));
+    static constexpr int BY_REGS = 1024 / THREADS;
+    static constexpr int MIN_BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
+    static_assert(OFF_META % 128 == 0 && OFF_ST % 128 == 0 && PKB_WT_WARPS <= 16, "TMA box destinations are 128-byte aligned");
+};
+static_assert(PKB_WT_SMALL <= 256 && PKB_WT_MID <= 256 && PKB_WT_LARGE <= 256, "list entries hold the slot in 8 bits");
+
+// run_further_hands for the warp-tile kernel: the control word travels in the list-E entry (slot | ctl << 8)
+template <int P>
+__device__ __noinline__ void run_further_hands_w(unsigned char* buf, uint32_t* entry, uint32_t* ep, size_t env, const StepArgs& a)
+{
+    using L = WarpTile<P>;
+    View<L::T> v = tile_view<L>(buf);
+    const DevState& d = a.d;
+    const int s = (int)(*entry & 255u);
+    Seats x = load_seats<P>(v, s);
+    Ctl c = unpack_ctl(*entry >> 8);
+    Meta m = unpack_meta(v.meta[s]);
+    uint32_t episode = ep[s];
+    unsigned long long hands = 0, shows = 0;
+    while (c.pc == PC_END_HAND) {
+        ++hands;
+        const bool ranked = end_hand_begin<P>(v, s, x, c);
+        if (!ranked && c.poisoned) break;
+        if (ranked) {
+            ++shows;
+            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode);
+        }
+        c.pc = PC_DONE;
+        double pay[P];
+        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) ep[s] = ++episode;
+        if (a.gc.track_stats)
+            for (int p = 0; p < P; ++p) atomicAdd(&d.payoff_sum[p], pay[p]);
+    }
+    if (a.gc.track_stats) {
+        atomicAdd(&d.stats[STAT_HANDS], hands);
+        atomicAdd(&d.stats[STAT_SHOWDOWNS], shows);
+    }
+    store_seats<P>(v, s, x);
+    v.meta[s] = pack_meta(m);
+    *entry = (uint32_t)s | pack_ctl(c) << 8;
+}
+
+template <int P, bool SAMPLE>
+__global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS) step_warp_kernel(const __grid_constant__ StepArgs a)
+{
+    using L = WarpTile<P>;
+    constexpr int T = L::T;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DevState& d = a.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* buf = smem + L::HEADER + (size_t)warp * L::WARP_BYTES;
+    const uint32_t bar = smem_u32(smem) + 8u * (uint32_t)warp, buf_s = smem_u32(buf);
+    uint32_t* list_e = reinterpret_cast<uint32_t*>(buf + L::OFF_LIST_E);
+    uint8_t* list_s = buf + L::OFF_LIST_S;
+    View<T> v = tile_view<L>(buf);
+    uint32_t* ep = reinterpret_cast<uint32_t*>(buf + L::OFF_EP);
+    const uint32_t lanes_below = (1u << lane) - 1u;
+
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+
+    Tally<P> tl;
+#pragma unroll
+    for (int p = 0; p < P; ++p) tl.pay[p] = 0.0;
+    tl.hands = tl.shows = tl.games = tl.poisoned = tl.invalid = tl.live = 0;
+
+    // the first tile of a warp is its global index; further tiles come from a global dispenser, drawn one tile ahead
+    const uint32_t warps_total = gridDim.x * PKB_WT_WARPS;
+    uint32_t tile = blockIdx.x * PKB_WT_WARPS + warp;
+    for (uint32_t it = 0; tile < a.num_tiles; ++it) {
+        const size_t base = (size_t)tile * T;
+        if (lane == 0) {  // three TMA box copies bring the tile in
+            mbar_arrive_expect_tx(bar, (uint32_t)L::BUF_BYTES);
+            tma_load_2d(buf_s + (uint32_t)L::OFF_CR, &a.maps.f64, (int)base, 0, bar);
+            tma_load_2d(buf_s + (uint32_t)L::OFF_META, &a.maps.u32, (int)base, 0, bar);
+            tma_load_2d(buf_s + (uint32_t)L::OFF_ST, &a.maps.u8, (int)base, 0, bar);
+        }
+        uint32_t next = 0;
+        if (lane == 0) next = warps_total + atomicAdd(&d.sched[0], 1u);  // consumed after the stores
+        mbar_wait(bar, it & 1u);
+
+        // ---- pass A: every slot
+        uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
+#pragma unroll 1
+        for (int s = lane; s < T; s += 32) {
+            const size_t env = base + s;
+            const bool live = env < d.n;
+            Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
+            if (live) {
+                Seats x = load_seats<P>(v, s);
+                Meta m = unpack_meta(v.meta[s]);
+                const double hb = high_bet<P>(v, s), credit = v.cr[m.act * T + s];
+                const uint32_t vm = valid_mask_from(hb, credit, v.mr[s]);
+                int action;
+                if (SAMPLE) {
+                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
+                    action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
+                    if (a.actions_out) a.actions_out[env] = action;
+                } else
+                    action = a.actions[env];
+                step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
+                const bool skipped = !SAMPLE && action == ACTION_SKIP;  // rejected like any out-of-range action, but not an error
+                tl.live += skipped ? 0u : 1u;
+                tl.invalid += skipped ? 0u : (uint32_t)c.invalid;
+                if (c.pc == PC_END_HAND) {  // end_hand's head (game.py:453-482): it is short, and it decides the list
+                    ++tl.hands;
+                    if (end_hand_begin<P>(v, s, x, c)) c.pc = PC_SHOWDOWN;
+                }
+                if (!c.invalid) {  // an invalid action changes nothing (game.py:649-651)
+                    store_seats<P>(v, s, x);
+                    v.meta[s] = pack_meta(m);
+                }
+                if (c.pc == PC_DONE) {
+                    tl.poisoned += (uint32_t)c.poisoned;
+                    write_outputs<P>(v, s, c, a, env, skipped);
+                }
+            }
+            const bool in_e = live && c.pc != PC_DONE, in_s = live && c.pc == PC_SHOWDOWN;
+            const uint32_t vote_e = __ballot_sync(FULL, in_e), vote_s = __ballot_sync(FULL, in_s);
+            if (in_e) list_e[n_e + (uint32_t)__popc(vote_e & lanes_below)] = (uint32_t)s | pack_ctl(c) << 8;
+            if (in_s) list_s[n_s + (uint32_t)__popc(vote_s & lanes_below)] = (uint8_t)s;
+            n_e += (uint32_t)__popc(vote_e);
+            n_s += (uint32_t)__popc(vote_s);
+        }
+        __syncwarp();
+
+        // ---- pass C: the ranked showdown for the slots in list S
+        for (uint32_t i = lane; i < n_s; i += 32) {
+            const int s = list_s[i];
+            const Seats x = load_seats<P>(v, s);
+            Ctl c{PC_SHOWDOWN, 0, 0, 0, 0, 0, 0, popc32(x.active | x.called | x.allin)};
+            ++tl.shows;
+            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+        }
+        __syncwarp();
+
+        // ---- pass D: the rest of end_hand and of the step for the slots in list E
+        for (uint32_t i = lane; i < n_e; i += 32) {
+            const uint32_t entry = list_e[i];
+            const int s = (int)(entry & 255u);
+            const size_t env = base + s;
+            Seats x = load_seats<P>(v, s);
+            Ctl c = unpack_ctl(entry >> 8);
+            Meta m = unpack_meta(v.meta[s]);
+            if (c.poisoned) {
+                // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
+                // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED
+#pragma unroll
+                for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
+                c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
+                c.pc = PC_DONE;
+            } else {
+                c.pc = PC_DONE;
+                double pay[P];
+                if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) ep[s] += 1;
+#pragma unroll
+                for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
+                store_seats<P>(v, s, x);
+                v.meta[s] = pack_meta(m);
+                if (c.pc == PC_END_HAND) {  // another hand ends inside this step
+                    list_e[i] = (uint32_t)s | pack_ctl(c) << 8;
+                    run_further_hands_w<P>(buf, &list_e[i], ep, env, a);
+                    c = unpack_ctl(list_e[i] >> 8);
+                    if (c.poisoned) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
+                        x = load_seats<P>(v, s);
+                        c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
+                        c.pc = PC_DONE;
+                    }
+                }
+            }
+            const uint32_t f = write_outputs<P>(v, s, c, a, env);
+            tl.games += (f & F_GAME_OVER) ? 1u : 0u;
+            tl.poisoned += (uint32_t)c.poisoned;
+        }
+
+        // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(&a.maps.f64, (int)base, 0, buf_s + (uint32_t)L::OFF_CR);
+            tma_store_2d(&a.maps.u32, (int)base, 0, buf_s + (uint32_t)L::OFF_META);
+            tma_store_2d(&a.maps.u8, (int)base, 0, buf_s + (uint32_t)L::OFF_ST);
+            bulk_commit();
+            bulk_wait_read();  // the buffer is about to be refilled
+        }
+        __syncwarp();
+        tile = __shfl_sync(FULL, next, 0);
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&d.sched[1], 1u) == gridDim.x - 1) {  // the last block to finish re-arms the dispenser
+        d.sched[0] = 0;
+        d.sched[1] = 0;
+    }
     if (a.gc.track_stats) reduce_stats<P>(d, tl);
 }
 
@@ -807,6 +1091,7 @@ __global__ void compare_kernel(const uint32_t* __restrict__ packed, int p, uint6
 using namespace pkb;
 
 struct pkb_env {
+    TileMaps maps;
     pkb_config cfg;
     DevState d;
     GameConst gc;
@@ -851,30 +1136,96 @@ static int fail(const char* what, cudaError_t e = cudaSuccess)
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // One launch per step: a persistent grid of as many blocks as fit the device at once.
+template <class K>
+static cudaError_t resident_blocks(K kernel, int threads, size_t smem, int device, int* cache)
+{
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (cache[device]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // the tiles want (almost) all of the SM's 228 KB as shared memory; without this the driver may pick a smaller
+    // carve-out, fewer blocks become resident than the persistent grid assumes, and the rest run as a second wave
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    cache[device] = nb;
+    return cudaSuccess;
+}
+
+// block-tile form (step_tile_kernel), kept for comparison: PKB_STEP_IMPL=tile
 template <int P, bool SAMPLE>
-static cudaError_t launch_step(const StepArgs& a, cudaStream_t s, int device, int sm_count)
+static cudaError_t launch_step_tile(StepArgs& a, cudaStream_t s, int device, int sm_count)
 {
     constexpr size_t smem = Tile<P>::BYTES;
     static int blocks_per_sm[64] = {0};
-    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
-    if (!blocks_per_sm[device]) {
-        cudaError_t e = cudaFuncSetAttribute(step_tile_kernel<P, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        // the tile ring wants (almost) all of the SM's 228 KB as shared memory; without this the driver may pick a
-        // smaller carve-out, fewer blocks become resident than the persistent grid assumes, and the rest run as a second wave
-        e = cudaFuncSetAttribute(step_tile_kernel<P, SAMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_tile_kernel<P, SAMPLE>, step_threads<P>(), smem);
-        if (e != cudaSuccess) return e;
-        if (nb < 1) return cudaErrorLaunchOutOfResources;
-        blocks_per_sm[device] = nb;
-    }
-    if (getenv("PKB_VERBOSE")) fprintf(stderr, "pkb: step kernel P=%d smem=%zu blocks/SM=%d\n", P, smem, blocks_per_sm[device]);
+    cudaError_t e = resident_blocks(step_tile_kernel<P, SAMPLE>, step_threads<P>(), smem, device, blocks_per_sm);
+    if (e != cudaSuccess) return e;
+    a.num_tiles = (uint32_t)((a.d.n + tile_envs<P>() - 1) / tile_envs<P>());
     const unsigned resident = (unsigned)(blocks_per_sm[device] * sm_count);
     const unsigned grid = a.num_tiles < resident ? a.num_tiles : resident;
     step_tile_kernel<P, SAMPLE><<<grid, step_threads<P>(), smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <int P, bool SAMPLE>
+static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_count)
+{
+    static const bool use_tile = getenv("PKB_STEP_IMPL") && !strcmp(getenv("PKB_STEP_IMPL"), "tile");
+    if (use_tile) return launch_step_tile<P, SAMPLE>(a, s, device, sm_count);
+    using L = WarpTile<P>;
+    static int blocks_per_sm[64] = {0};
+    cudaError_t e = resident_blocks(step_warp_kernel<P, SAMPLE>, L::THREADS, L::BYTES, device, blocks_per_sm);
+    if (e != cudaSuccess) return e;
+    if (getenv("PKB_VERBOSE"))
+        fprintf(stderr, "pkb: step kernel P=%d warp tile=%d smem=%zu blocks/SM=%d (compiled for %d)\n", P, L::T, (size_t)L::BYTES,
+                blocks_per_sm[device], L::MIN_BLOCKS);
+    a.num_tiles = (uint32_t)((a.d.n + L::T - 1) / L::T);
+    const unsigned resident = (unsigned)(blocks_per_sm[device] * sm_count);
+    const unsigned want = (a.num_tiles + PKB_WT_WARPS - 1) / PKB_WT_WARPS;
+    step_warp_kernel<P, SAMPLE><<<want < resident ? want : resident, L::THREADS, L::BYTES, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- TMA descriptors (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [rows][stride] plane group of `elem`-byte elements, box = [rows][tile]
+static bool make_plane_map(CUtensorMap* m, CUtensorMapDataType type, size_t elem, void* base, uint64_t stride, uint32_t rows, uint32_t tile)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {stride, rows};
+    const cuuint64_t strides[1] = {stride * elem};
+    const cuuint32_t box[2] = {tile, rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, type, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int P>
+static bool make_tile_maps(TileMaps& maps, const DevState& d)
+{
+    using L = WarpTile<P>;
+    return make_plane_map(&maps.f64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, d.cr, d.stride, L::F64_ROWS, L::T) &&
+           make_plane_map(&maps.u32, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, d.meta, d.stride, L::U32_ROWS, L::T) &&
+           make_plane_map(&maps.u8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d.st, d.stride, P, L::T);
 }
 
 extern "C" {
@@ -945,8 +1296,8 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     d.cr = f;
     d.bt = f + (size_t)P * stride;
     d.pd = f + (size_t)2 * P * stride;
-    d.payoffs = f + (size_t)3 * P * stride;
-    d.mr = f + (size_t)4 * P * stride;
+    d.mr = f + (size_t)3 * P * stride;  // right after pending_bets: credits..minimum_raise are one 2-D TMA tensor of 3P+1 rows
+    d.payoffs = f + (size_t)(3 * P + 1) * stride;
     uint32_t* u = reinterpret_cast<uint32_t*>(base + off_u32);
     d.meta = u;
     d.hand = u + stride;
@@ -975,6 +1326,13 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
         delete h;
         return fail("pkb_create: cudaDeviceGetAttribute", e);
     }
+    bool maps_ok = false;
+    PKB_DISPATCH_P(P, fill_fresh_state<P>(gc); maps_ok = make_tile_maps<P>(h->maps, d));
+    if (!maps_ok) {
+        cudaFree(h->arena);
+        delete h;
+        return fail("pkb_create: cuTensorMapEncodeTiled failed");
+    }
     *out = h;
     return 0;
 }
@@ -994,6 +1352,7 @@ int pkb_set_reset_dealer(pkb_env* h, int32_t dealer)
     if (dealer < 0 || dealer >= h->cfg.num_players) return fail("pkb_set_reset_dealer: dealer out of range");
     h->cfg.dealer = dealer;
     h->gc.dealer = dealer;
+    PKB_DISPATCH_P(h->cfg.num_players, fill_fresh_state<P>(h->gc));
     return 0;
 }
 
@@ -1014,6 +1373,7 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     if (!sample && !actions) return fail("pkb_step: null actions");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     StepArgs a;
+    a.maps = h->maps;
     a.d = h->d;
     a.gc = h->gc;
     a.actions = actions;
@@ -1026,7 +1386,6 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaSuccess;
     PKB_DISPATCH_P(h->cfg.num_players,
-                   a.num_tiles = (uint32_t)((h->d.n + tile_envs<P>() - 1) / tile_envs<P>());
                    e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count)
                               : launch_step<P, false>(a, s, h->cfg.device, h->sm_count));
     if (e != cudaSuccess) return fail("pkb_step: launch", e);

@@ -22,7 +22,8 @@ struct U4 {
     uint32_t x, y, z, w;
 };
 
-PKB_HD_CALL U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+// inlined form: several independent blocks of one thread interleave (the deal of a showdown)
+PKB_HD U4 philox4x32_10_inl(U4 c, uint32_t k0, uint32_t k1)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -34,6 +35,7 @@ PKB_HD_CALL U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
     }
     return c;
 }
+PKB_HD_CALL U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) { return philox4x32_10_inl(c, k0, k1); }
 
 // position of the j-th (0-based) set bit of a 52-bit mask; j < popcount(f)
 PKB_HD_CALL uint32_t select_bit(uint64_t f, uint32_t j)
@@ -76,6 +78,37 @@ struct Dealer {
         return id;
     }
 };
+
+// The same deal for small tables, all draws at once: the N = 5+2P card ids of (seed, env, episode, hand).
+// The Philox blocks are independent and interleave; the draw chain keeps the ids drawn so far SORTED as
+// t[j] = (j-th smallest id) - j (non-decreasing), so that "the r-th smallest id not drawn yet" is
+// r + #{j : t[j] <= r} -- independent compares instead of a six-level popcount search per draw.
+template <int N>
+PKB_HD void deal_ids(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t hand, uint32_t (&id)[N])
+{
+    constexpr int NB = (N + 3) / 4;
+    uint32_t word[NB * 4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const U4 blk = philox4x32_10_inl(U4{env_id, hand, episode, (uint32_t)b}, (uint32_t)seed, (uint32_t)(seed >> 32));
+        word[4 * b] = blk.x; word[4 * b + 1] = blk.y; word[4 * b + 2] = blk.z; word[4 * b + 3] = blk.w;
+    }
+    uint32_t t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t r = mulhi32(word[i], (uint32_t)(52 - i));
+        uint32_t k = 0;
+#pragma unroll
+        for (int j = 0; j < i; ++j) k += t[j] <= r ? 1u : 0u;
+        id[i] = r + k;
+        // insert at position k: the entries from k on move up one place, and their value drops by one
+#pragma unroll
+        for (int j = i; j >= 0; --j) {
+            const uint32_t below = j > 0 ? t[j > 0 ? j - 1 : 0] - 1u : 0u;
+            t[j] = (uint32_t)j > k ? below : (uint32_t)j == k ? r : t[j];
+        }
+    }
+}
 
 // the 32-bit word that drives the action draw of (env, step): a pure function, independent of the state
 PKB_HD uint32_t sample_word(uint64_t seed, uint32_t env_id, uint32_t step_idx)

@@ -34,6 +34,19 @@ uint64_t hc_eval_tbl_mismatches(int k, uint64_t count)
     }
     return bad;
 }
+// the select form used inside the step kernels against the bitmask evaluator, same enumeration
+uint32_t hc_eval_mask_sel(uint64_t m) { return pkb::eval_mask52_sel(m); }
+uint64_t hc_eval_sel_mismatches(int k, uint64_t first_index_unused, uint64_t count)
+{
+    (void)first_index_unused;
+    uint64_t m = (1ull << k) - 1, bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        bad += pkb::eval_mask52_sel(m) != pkb::eval_mask52(m);
+        const uint64_t c = m & -m, r = m + c;
+        m = (((r ^ m) >> 2) / c) | r;
+    }
+    return bad;
+}
 uint32_t hc_eval_cards(const uint8_t* c, int n) { return pkb::eval_cards(c, n); }
 uint32_t hc_eval_cards_literal(const uint8_t* c, int n) { return pkb::eval_cards_literal(c, n); }
 
@@ -66,6 +79,21 @@ void hc_deal(uint64_t seed, uint32_t env, uint32_t episode, uint32_t hand, int P
 {
     pkb::Dealer d(seed, env, episode, hand);
     for (int i = 0; i < 5 + 2 * P; ++i) out[i] = (uint8_t)pkb::card_value_from_id(d.next());
+}
+
+// the all-at-once deal of the step kernels (small tables): must equal the sequential Dealer
+int hc_deal_ids(uint64_t seed, uint32_t env, uint32_t episode, uint32_t hand, int P, uint8_t* out)
+{
+    uint32_t id[13];
+    switch (P) {
+        case 1: { uint32_t a[7]; pkb::deal_ids<7>(seed, env, episode, hand, a); for (int i = 0; i < 7; ++i) id[i] = a[i]; } break;
+        case 2: { uint32_t a[9]; pkb::deal_ids<9>(seed, env, episode, hand, a); for (int i = 0; i < 9; ++i) id[i] = a[i]; } break;
+        case 3: { uint32_t a[11]; pkb::deal_ids<11>(seed, env, episode, hand, a); for (int i = 0; i < 11; ++i) id[i] = a[i]; } break;
+        case 4: { uint32_t a[13]; pkb::deal_ids<13>(seed, env, episode, hand, a); for (int i = 0; i < 13; ++i) id[i] = a[i]; } break;
+        default: return -1;
+    }
+    for (int i = 0; i < 5 + 2 * P; ++i) out[i] = (uint8_t)pkb::card_value_from_id(id[i]);
+    return 0;
 }
 
 int hc_sample(uint64_t seed, uint32_t env, uint32_t step, uint32_t valid, const uint32_t* w)

@@ -53,6 +53,33 @@ def test_table_evaluator_equals_bitmask_evaluator(hc, ora, k):
     assert hc.hc_eval_mask_tbl(0) == int(ora.eval_masks_batch(np.zeros(1, dtype=np.uint64))[0])
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7])
+def test_select_evaluator_equals_bitmask_evaluator(hc, k):
+    """The select-only form the step kernels inline (pkb_eval.cuh eval_mask52_sel) returns exactly what the bitmask
+    evaluator returns: all C(52,k) hands for k <= 6, the first 8M seven-card hands."""
+    import math
+    count = math.comb(52, k) if k <= 6 else 8_000_000
+    hc.hc_eval_sel_mismatches.restype = C.c_uint64
+    hc.hc_eval_sel_mismatches.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
+    assert hc.hc_eval_sel_mismatches(k, 0, count) == 0
+    hc.hc_eval_mask_sel.restype = C.c_uint32
+    hc.hc_eval_mask_sel.argtypes = [C.c_uint64]
+    assert hc.hc_eval_mask_sel(0) == 10 << 20
+
+
+def test_all_at_once_deal_equals_sequential_dealer(hc):
+    """deal_ids (interleaved Philox blocks + sorted draw chain, P <= 4) deals exactly the cards of the sequential Dealer."""
+    rng = np.random.default_rng(3)
+    hc.hc_deal_ids.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    for P in (1, 2, 3, 4):
+        for _ in range(20000):
+            seed = int(rng.integers(0, 2**63)); env = int(rng.integers(0, 2**32)); ep = int(rng.integers(0, 2**20)); hand = int(rng.integers(0, 2**16))
+            a = np.zeros(5 + 2 * P, dtype=np.uint8); b = np.zeros(5 + 2 * P, dtype=np.uint8)
+            hc.hc_deal(seed, env, ep, hand, P, a.ctypes.data)
+            assert hc.hc_deal_ids(seed, env, ep, hand, P, b.ctypes.data) == 0
+            assert np.array_equal(a, b), (P, seed, env, ep, hand, a, b)
+
+
 def test_product_card_list_paths(hc, ora, golden_dir):
     d = np.load(os.path.join(golden_dir, "eval_vectors.npz"))
     for c, k, p in zip(d["cards"], d["counts"], d["packed"]):
