@@ -188,6 +188,10 @@ PKB_D void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src_sme
                  "r"(src_smem)
                  : "memory");
 }
+PKB_D void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1)  // pull a box into L2 ahead of its load
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 PKB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 PKB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -322,6 +326,7 @@ PKB_D void reduce_stats(const DevState& d, const Tally<P>& tl)
 #ifdef PKB_TIMING
 __device__ unsigned long long g_span[3] = {~0ull, 0ull, 0ull};  // globaltimer: earliest block start, latest block start, latest block end
 __device__ unsigned long long g_blk[2048][4];  // per block of the last launch: start ns, end ns, SM id, tiles
+__device__ unsigned long long g_wrp[4096][12];  // per warp of the last warp-tile launch: start ns, end ns, SM id, 5 phase cycle sums, tiles
 __device__ unsigned long long g_timing[8];  // cycles as seen by thread 0: load wait, A, C, D, store issue, whole block, tiles
 #define PKB_TICK(i)                                        \
     do {                                                   \
@@ -620,6 +625,7 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
 #ifndef PKB_WT_WARPS
 #define PKB_WT_WARPS 4    // warps per block (they only share the block's statistics reduction)
 #endif
+
 static_assert(STRIDE_ALIGN % PKB_WT_SMALL == 0 && STRIDE_ALIGN % PKB_WT_MID == 0 && STRIDE_ALIGN % PKB_WT_LARGE == 0, "warp tiles must divide the plane stride");
 
 template <int P>
@@ -659,42 +665,6 @@ struct WarpTile {
 };
 static_assert(PKB_WT_SMALL <= 256 && PKB_WT_MID <= 256 && PKB_WT_LARGE <= 256, "list entries hold the slot in 8 bits");
 
-// run_further_hands for the warp-tile kernel: the control word travels in the list-E entry (slot | ctl << 8)
-template <int P>
-__device__ __noinline__ void run_further_hands_w(unsigned char* buf, uint32_t* entry, uint32_t* ep, size_t env, const StepArgs& a)
-{
-    using L = WarpTile<P>;
-    View<L::T> v = tile_view<L>(buf);
-    const DevState& d = a.d;
-    const int s = (int)(*entry & 255u);
-    Seats x = load_seats<P>(v, s);
-    Ctl c = unpack_ctl(*entry >> 8);
-    Meta m = unpack_meta(v.meta[s]);
-    uint32_t episode = ep[s];
-    unsigned long long hands = 0, shows = 0;
-    while (c.pc == PC_END_HAND) {
-        ++hands;
-        const bool ranked = end_hand_begin<P>(v, s, x, c);
-        if (!ranked && c.poisoned) break;
-        if (ranked) {
-            ++shows;
-            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode);
-        }
-        c.pc = PC_DONE;
-        double pay[P];
-        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) ep[s] = ++episode;
-        if (a.gc.track_stats)
-            for (int p = 0; p < P; ++p) atomicAdd(&d.payoff_sum[p], pay[p]);
-    }
-    if (a.gc.track_stats) {
-        atomicAdd(&d.stats[STAT_HANDS], hands);
-        atomicAdd(&d.stats[STAT_SHOWDOWNS], shows);
-    }
-    store_seats<P>(v, s, x);
-    v.meta[s] = pack_meta(m);
-    *entry = (uint32_t)s | pack_ctl(c) << 8;
-}
-
 template <int P, bool SAMPLE>
 __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS) step_warp_kernel(const __grid_constant__ StepArgs a)
 {
@@ -720,6 +690,21 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     for (int p = 0; p < P; ++p) tl.pay[p] = 0.0;
     tl.hands = tl.shows = tl.games = tl.poisoned = tl.invalid = tl.live = 0;
 
+#ifdef PKB_TIMING
+    unsigned long long wt_acc[6] = {0, 0, 0, 0, 0, 0};  // cycles: load wait, pass A, pass C, pass D, store; tiles
+    unsigned long long wt_rounds = 0, wt_maxc = 0, wt_maxns = 0;
+    unsigned long long wt_gt0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wt_gt0));
+    long long wt_last = clock64();
+#define PKB_WTICK(i)                                             \
+    do {                                                         \
+        const long long now_ = clock64();                        \
+        wt_acc[i] += (unsigned long long)(now_ - wt_last);       \
+        wt_last = now_;                                          \
+    } while (0)
+#else
+#define PKB_WTICK(i)
+#endif
     // the first tile of a warp is its global index; further tiles come from a global dispenser, drawn one tile ahead
     const uint32_t warps_total = gridDim.x * PKB_WT_WARPS;
     uint32_t tile = blockIdx.x * PKB_WT_WARPS + warp;
@@ -732,8 +717,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             tma_load_2d(buf_s + (uint32_t)L::OFF_ST, &a.maps.u8, (int)base, 0, bar);
         }
         uint32_t next = 0;
-        if (lane == 0) next = warps_total + atomicAdd(&d.sched[0], 1u);  // consumed after the stores
+        if (lane == 0) next = atomicAdd(&d.sched[0], 1u);  // consumed after the stores
         mbar_wait(bar, it & 1u);
+        PKB_WTICK(0);
 
         // ---- pass A: every slot
         uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
@@ -779,61 +765,99 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             n_s += (uint32_t)__popc(vote_s);
         }
         __syncwarp();
-
-        // ---- pass C: the ranked showdown for the slots in list S
-        for (uint32_t i = lane; i < n_s; i += 32) {
-            const int s = list_s[i];
-            const Seats x = load_seats<P>(v, s);
-            Ctl c{PC_SHOWDOWN, 0, 0, 0, 0, 0, 0, popc32(x.active | x.called | x.allin)};
-            ++tl.shows;
-            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+        PKB_WTICK(1);
+#ifndef PKB_WT_NO_PREFETCH
+        // The next tile is known by now (the dispenser answered during pass A): start it on its way into L2, so
+        // that the load after this tile's stores finds it there instead of waiting on HBM with the buffer empty.
+        if (lane == 0 && warps_total + next < a.num_tiles) {
+            const int nb = (int)((warps_total + next) * (uint32_t)T);
+            tma_prefetch_2d(&a.maps.f64, nb, 0);
+            tma_prefetch_2d(&a.maps.u32, nb, 0);
+            tma_prefetch_2d(&a.maps.u8, nb, 0);
         }
-        __syncwarp();
+#endif
 
-        // ---- pass D: the rest of end_hand and of the step for the slots in list E
-        for (uint32_t i = lane; i < n_e; i += 32) {
-            const uint32_t entry = list_e[i];
-            const int s = (int)(entry & 255u);
-            const size_t env = base + s;
-            Seats x = load_seats<P>(v, s);
-            Ctl c = unpack_ctl(entry >> 8);
-            Meta m = unpack_meta(v.meta[s]);
-            if (c.poisoned) {
-                // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
-                // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED
-#pragma unroll
-                for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
-                c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
-                c.pc = PC_DONE;
-            } else {
-                c.pc = PC_DONE;
-                double pay[P];
-                if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) ep[s] += 1;
-#pragma unroll
-                for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
-                store_seats<P>(v, s, x);
-                v.meta[s] = pack_meta(m);
-                if (c.pc == PC_END_HAND) {  // another hand ends inside this step
-                    list_e[i] = (uint32_t)s | pack_ctl(c) << 8;
-                    run_further_hands_w<P>(buf, &list_e[i], ep, env, a);
-                    c = unpack_ctl(list_e[i] >> 8);
+        // Passes C and D repeat while hands keep ending inside this step (all-in blinds: a slot whose next hand
+        // cannot be acted on either); such slots go round again through the SAME code, side by side.
+        while (n_e) {
+#ifdef PKB_TIMING
+            const long long wt_c0 = clock64();
+            wt_rounds += 1;
+            wt_maxns = n_s > wt_maxns ? n_s : wt_maxns;
+#endif
+            // ---- pass C: the ranked showdown for the slots in list S
+            for (uint32_t i = lane; i < n_s; i += 32) {
+                const int s = list_s[i];
+                const Seats x = load_seats<P>(v, s);
+                Ctl c{PC_SHOWDOWN, 0, 0, 0, 0, 0, 0, popc32(x.active | x.called | x.allin)};
+                ++tl.shows;
+                showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+            }
+            __syncwarp();
+            PKB_WTICK(2);
+#ifdef PKB_TIMING
+            if ((unsigned long long)(clock64() - wt_c0) > wt_maxc) wt_maxc = (unsigned long long)(clock64() - wt_c0);
+#endif
+
+            // ---- pass D: the rest of end_hand and of the step for the slots in list E.  A slot in which another hand
+            // ends is appended to the lists of the next round, in place: at most as many entries are written as were
+            // read, and every lane has read its entry before the ballot that precedes the writes.
+            uint32_t m_e = 0, m_s = 0;
+            for (uint32_t i0 = 0; i0 < n_e; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                bool again = false, again_s = false;
+                uint32_t entry = 0;
+                if (i < n_e) {
+                    entry = list_e[i];
+                    const int s = (int)(entry & 255u);
+                    const size_t env = base + s;
+                    Seats x = load_seats<P>(v, s);
+                    Ctl c = unpack_ctl(entry >> 8);
+                    Meta m = unpack_meta(v.meta[s]);
                     if (c.poisoned) {
+                        // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
+                        // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED
 #pragma unroll
                         for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
-                        x = load_seats<P>(v, s);
                         c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
                         c.pc = PC_DONE;
+                    } else {
+                        c.pc = PC_DONE;
+                        double pay[P];
+                        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) ep[s] += 1;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
+                        if (c.pc == PC_END_HAND) {  // another hand ends inside this step: its head now, the rest next round
+                            ++tl.hands;
+                            again = true;
+                            again_s = end_hand_begin<P>(v, s, x, c);
+                            if (again_s) c.pc = PC_SHOWDOWN;
+                            entry = (uint32_t)s | pack_ctl(c) << 8;
+                        }
+                        store_seats<P>(v, s, x);
+                        v.meta[s] = pack_meta(m);
+                    }
+                    if (!again) {
+                        const uint32_t f = write_outputs<P>(v, s, c, a, env);
+                        tl.games += (f & F_GAME_OVER) ? 1u : 0u;
+                        tl.poisoned += (uint32_t)c.poisoned;
                     }
                 }
+                const uint32_t vote_e = __ballot_sync(FULL, again), vote_s = __ballot_sync(FULL, again_s);
+                if (again) list_e[m_e + (uint32_t)__popc(vote_e & lanes_below)] = entry;
+                if (again_s) list_s[m_s + (uint32_t)__popc(vote_s & lanes_below)] = (uint8_t)(entry & 255u);
+                m_e += (uint32_t)__popc(vote_e);
+                m_s += (uint32_t)__popc(vote_s);
             }
-            const uint32_t f = write_outputs<P>(v, s, c, a, env);
-            tl.games += (f & F_GAME_OVER) ? 1u : 0u;
-            tl.poisoned += (uint32_t)c.poisoned;
+            __syncwarp();
+            n_e = m_e;
+            n_s = m_s;
         }
 
         // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
         fence_async_smem();
         __syncwarp();
+        PKB_WTICK(3);
         if (lane == 0) {
             tma_store_2d(&a.maps.f64, (int)base, 0, buf_s + (uint32_t)L::OFF_CR);
             tma_store_2d(&a.maps.u32, (int)base, 0, buf_s + (uint32_t)L::OFF_META);
@@ -842,9 +866,31 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             bulk_wait_read();  // the buffer is about to be refilled
         }
         __syncwarp();
-        tile = __shfl_sync(FULL, next, 0);
+        tile = warps_total + __shfl_sync(FULL, next, 0);
+        PKB_WTICK(4);
+#ifdef PKB_TIMING
+        wt_acc[5] += 1;
+#endif
     }
     if (lane == 0) bulk_wait_all();
+#ifdef PKB_TIMING
+    {
+        const uint32_t gw = blockIdx.x * PKB_WT_WARPS + warp;
+        if (lane == 0 && gw < 4096) {
+            unsigned long long gt1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_wrp[gw][0] = wt_gt0;
+            g_wrp[gw][1] = gt1;
+            g_wrp[gw][2] = smid;
+            for (int i = 0; i < 6; ++i) g_wrp[gw][3 + i] = wt_acc[i];
+            g_wrp[gw][9] = wt_rounds;
+            g_wrp[gw][10] = wt_maxc;
+            g_wrp[gw][11] = wt_maxns;
+        }
+    }
+#endif
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(&d.sched[1], 1u) == gridDim.x - 1) {  // the last block to finish re-arms the dispenser
         d.sched[0] = 0;
@@ -1238,6 +1284,7 @@ int pkb_debug_timing(unsigned long long* out)
     if (cudaMemcpyFromSymbol(out, g_timing, sizeof zero) != cudaSuccess) return -1;
     return cudaMemcpyToSymbol(g_timing, zero, sizeof zero) == cudaSuccess ? 0 : -1;
 }
+int pkb_debug_warps(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_wrp, sizeof(unsigned long long) * 4096 * 12) == cudaSuccess ? 0 : -1; }
 int pkb_debug_blocks(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_blk, sizeof(unsigned long long) * 2048 * 4) == cudaSuccess ? 0 : -1; }
 int pkb_debug_span(unsigned long long* out)
 {
