@@ -356,7 +356,8 @@ void ora_deal(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t hand, i
 }
 
 /*
- * Action sampling spec: counter {env_id, step_idx, 0, 0x80000000}; word 0;
+ * Action sampling spec: counter {env_id & ~96, step_idx, 0, 0x80000000}; word (env_id >> 5) & 3
+ * (the four envs whose ids differ only in bits 5 and 6 share one Philox block, one word each);
  * t = mulhi32(word, W) where W = sum of weights of valid actions; the chosen
  * action is the first valid a with cumulative weight > t.  Uniform = all 1
  * (RandomAgent, agents/random.py:16-17, is uniform over the valid actions).
@@ -364,12 +365,13 @@ void ora_deal(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t hand, i
 int ora_sample_action(uint64_t seed, uint32_t env_id, uint32_t step_idx, unsigned valid_mask, const uint32_t *weights)
 {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t ctr[4] = {env_id, step_idx, 0u, 0x80000000u}, out[4];
+    uint32_t ctr[4] = {env_id & ~96u, step_idx, 0u, 0x80000000u}, out[4];
     ora_philox4x32_10(ctr, key, out);
+    const uint32_t word = out[env_id >> 5 & 3u];
     uint32_t total = 0;
     for (int a = 0; a < ORA_NUM_MOVES; ++a)
         if (valid_mask >> a & 1) total += weights ? weights[a] : 1u;
-    uint32_t t = (uint32_t)(((uint64_t)out[0] * (uint64_t)total) >> 32), acc = 0;
+    uint32_t t = (uint32_t)(((uint64_t)word * (uint64_t)total) >> 32), acc = 0;
     for (int a = 0; a < ORA_NUM_MOVES; ++a)
         if (valid_mask >> a & 1) {
             acc += weights ? weights[a] : 1u;

@@ -723,6 +723,12 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 
         // ---- pass A: every slot
         uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
+        // the action draws of a lane's slots come from ONE Philox block when the tile starts on a multiple of 128 (or of
+        // 64 for the 64-env tiles) in global env ids, which it does unless env_id_base is odd-sized (pkb_philox.cuh)
+        const uint32_t gid0 = a.gc.env_id_base + (uint32_t)base + (uint32_t)lane;
+        const bool shared_draw = SAMPLE && T <= 128 && ((a.gc.env_id_base + (uint32_t)base) & (uint32_t)(T - 1)) == 0;
+        U4 draw{0, 0, 0, 0};
+        if (shared_draw) draw = sample_block(a.gc.seed, gid0, a.step_idx);
 #pragma unroll 1
         for (int s = lane; s < T; s += 32) {
             const size_t env = base + s;
@@ -735,7 +741,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 const uint32_t vm = valid_mask_from(hb, credit, v.mr[s]);
                 int action;
                 if (SAMPLE) {
-                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
+                    const uint32_t gid = a.gc.env_id_base + (uint32_t)env;
+                    const uint32_t word = shared_draw ? sample_word_of(draw, gid) : sample_word(a.gc.seed, gid, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     if (a.actions_out) a.actions_out[env] = action;
                 } else

@@ -10,8 +10,10 @@
 // selects the j-th smallest card id not drawn yet.  Draws 0..4 are the board (game.py:278),
 // draws 5+2p, 6+2p the hole cards of seat p (game.py:385-389).
 //
-// Action spec: counter {env_id, step_idx, 0, 0x80000000}, word 0; t = mulhi32(word, W) with
-// W = total weight of the valid moves; the move is the first valid one whose cumulative
+// Action spec: counter {env_id & ~96, step_idx, 0, 0x80000000}, word (env_id >> 5) & 3 -- the four envs whose
+// ids differ only in bits 5 and 6 share one Philox block and take one word each, so a lane of the step kernel,
+// which handles exactly such envs (slots lane, lane+32, lane+64, lane+96 of a 128-env tile), computes one
+// block per tile instead of four.  t = mulhi32(word, W) with W = total weight of the valid moves; the move is the first valid one whose cumulative
 // weight exceeds t (uniform weights = RandomAgent, agents/random.py:16-17).
 #pragma once
 #include "pkb_common.cuh"
@@ -111,9 +113,18 @@ PKB_HD void deal_ids(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t 
 }
 
 // the 32-bit word that drives the action draw of (env, step): a pure function, independent of the state
+PKB_HD U4 sample_block(uint64_t seed, uint32_t env_id, uint32_t step_idx)  // shared by env_id, env_id ^ 32, ^ 64, ^ 96
+{
+    return philox4x32_10(U4{env_id & ~96u, step_idx, 0u, 0x80000000u}, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+PKB_HD uint32_t sample_word_of(const U4& b, uint32_t env_id)
+{
+    const uint32_t k = env_id >> 5 & 3u;
+    return k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w;
+}
 PKB_HD uint32_t sample_word(uint64_t seed, uint32_t env_id, uint32_t step_idx)
 {
-    return philox4x32_10(U4{env_id, step_idx, 0u, 0x80000000u}, (uint32_t)seed, (uint32_t)(seed >> 32)).x;
+    return sample_word_of(sample_block(seed, env_id, step_idx), env_id);
 }
 
 // weighted choice over the valid mask: the first valid move whose cumulative weight exceeds t
