@@ -8,7 +8,7 @@
 Workload (BASELINE.json configs[2]): heads-up NLHE, 2^20 lockstep envs PER GPU, start_credits 100, blinds
 2/1, uniform random agents drawn on device from Philox(seed 0, global env id, step), auto-reset on
 game over.  One bench "step" = one Game.step on every env = one launch of the fused
-sample+step kernel (pkb::step_tile_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective
+sample+step kernel (pkb::step_warp_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective
 (weak scaling); one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
 
 Timing: W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket, timed with
@@ -332,19 +332,18 @@ def run_ours(args, rank, local_rank, world):
     for j in range(RESIDENT_BATCHES):
         rec = make_batch(j)
         rec.reset()
-        ha = torch.empty((R, N), dtype=torch.int32).pin_memory()
+        ha = torch.empty((R, N), dtype=torch.uint8).pin_memory()  # one byte per action (pkb_step_u8)
         for r in range(R):
             rec.step_random(r, record_actions=True)
-            ha[r].copy_(rec.actions_taken)
+            ha[r].copy_(rec.actions_taken.to(torch.uint8))
         torch.cuda.synchronize()
         del rec
         host_actions.append(ha)
         run = make_batch(j)
         run.reset()
         runs.append(run)
-    dev_actions = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(RESIDENT_BATCHES)]
-    host_flags = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(RESIDENT_BATCHES)]
-    host_valid = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(RESIDENT_BATCHES)]
+    dev_actions = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(RESIDENT_BATCHES)]
+    host_out = [torch.empty((2, N), dtype=torch.uint8).pin_memory() for _ in range(RESIDENT_BATCHES)]  # flags, valid
     barrier()
     t0 = time.perf_counter()
     for st in streams:
@@ -353,9 +352,8 @@ def run_ours(args, rank, local_rank, world):
         for j in range(RESIDENT_BATCHES):
             with torch.cuda.stream(streams[j]):
                 dev_actions[j].copy_(host_actions[j][r], non_blocking=True)
-                flags, valid = runs[j].step(dev_actions[j])
-                host_flags[j].copy_(flags, non_blocking=True)
-                host_valid[j].copy_(valid, non_blocking=True)
+                runs[j].step(dev_actions[j])
+                host_out[j].copy_(runs[j].outputs, non_blocking=True)
     for st in streams:
         st.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -403,18 +401,18 @@ def run_ours(args, rank, local_rank, world):
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(N, world),
-        "roofline": {"bound": "hbm", "kernel": "pkb::step_tile_kernel<2,true>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "pkb::step_warp_kernel<2,true>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("step_kernel_p2"),
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_step(P),
                      "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
                      "avg_launch_note": "timed region / launches; the launches of the three resident batches run on three streams and overlap",
                      "isolated_launch_us": isolated_ms * 1e3, "isolated_achieved": bytes_per_launch / (isolated_ms / 1e3) / 1e9,
                      "isolated_frac": bytes_per_launch / (isolated_ms / 1e3) / 1e9 / peak, "peak_source": peak_src},
-        "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N,
+        "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": N,
                 "d2h_bytes_per_step": 2 * N, "steps": E,
-                "path": "per step: actions H2D from pinned host -> GameBatch.step -> pkb_step -> flags+valid D2H to pinned host; "
+                "path": "per step: one byte per action H2D from pinned host -> GameBatch.step -> pkb_step_u8 -> flags+valid D2H (one copy) to pinned host; "
                         "the three resident batches take turns on three streams, host synchronises at the end"},
-        "gpu_launches": K,  # one persistent step_tile_kernel launch per step
+        "gpu_launches": K,  # one persistent step_warp_kernel launch per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",
                         "note": "one batch stepped back to back: its 86 MB of state stays in the 126 MB L2"},

@@ -113,6 +113,11 @@ int pkb_set_reset_dealer(pkb_env *h, int32_t dealer);
 /* Game.step, game.py:621-700 on every env.  actions: device i32[N].  flags/valid: device u8[N] out
  * (valid = bit a set iff move a is valid for the NEW active player, game.py:339-383); either may be NULL. */
 int pkb_step(pkb_env *h, const int32_t *actions, uint8_t *flags, uint8_t *valid, void *stream);
+/* Same with one byte per action (a move index 0..6; PKB_ACTION_SKIP_U8 leaves the env alone; any other value is
+ * rejected like an out-of-range int, game.py:649-651): a quarter of the host-to-device bytes of pkb_step for callers
+ * whose actions come from the host every step. */
+#define PKB_ACTION_SKIP_U8 255
+int pkb_step_u8(pkb_env *h, const uint8_t *actions, uint8_t *flags, uint8_t *valid, void *stream);
 /* Same, with the action drawn on device: weighted choice over the valid mask from
  * Philox(seed, env_id, step_idx) (RandomAgent, agents/random.py:16-17 when weights == NULL).
  * weights: host u32[7] or NULL.  actions_out: device i32[N] or NULL (the actions taken, for replay). */

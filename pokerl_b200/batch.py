@@ -80,8 +80,9 @@ class GameBatch:
         self._h = _Handle(h)
         self._wrap_state()
         with torch.cuda.device(self.device):
-            self.flags = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
-            self.valid = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            # one [2, N] buffer (row 0 flags, row 1 valid masks): a caller that wants both on the host copies them at once
+            self.outputs = torch.zeros((2, self.num_envs), dtype=torch.uint8, device=self.device)
+            self.flags, self.valid = self.outputs[0], self.outputs[1]
             self.actions_taken = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
 
     # ---- zero-copy state ---------------------------------------------------------------------
@@ -149,11 +150,15 @@ class GameBatch:
         nat.check(nat.lib().pkb_reset(self._h.ptr, nat.ptr(env_mask), self._stream()))
 
     def step(self, actions, flags=None, valid=None):
-        """Game.step(actions[i]) on env i.  actions: int32 [N] on this device.  Returns (flags, valid)."""
-        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
-            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        """Game.step(actions[i]) on env i.  actions: int32 [N] on this device, or uint8 [N] (one byte per move index,
+        255 = skip: a quarter of the bytes when the actions come from the host).  Returns (flags, valid)."""
         flags = self.flags if flags is None else flags
         valid = self.valid if valid is None else valid
+        if actions.dtype == torch.uint8 and actions.device == self.device and actions.is_contiguous():
+            nat.check(nat.lib().pkb_step_u8(self._h.ptr, nat.ptr(actions), nat.ptr(flags), nat.ptr(valid), self._stream()))
+            return flags, valid
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
         nat.check(nat.lib().pkb_step(self._h.ptr, nat.ptr(actions), nat.ptr(flags), nat.ptr(valid), self._stream()))
         return flags, valid
 

@@ -49,6 +49,7 @@ struct StepArgs {
     DevState d;
     GameConst gc;
     const int32_t* actions;
+    const uint8_t* actions_u8;  // compact form of `actions` (255 = skip); used when `actions` is null
     int32_t* actions_out;
     uint8_t* flags;
     uint8_t* valid;
@@ -455,8 +456,12 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
                     const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     if (a.actions_out) a.actions_out[env] = action;
-                } else
+                } else if (a.actions)
                     action = a.actions[env];
+                else {
+                    action = a.actions_u8[env];
+                    action = action == 255 ? ACTION_SKIP : action;
+                }
                 step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
                 const bool skipped = !SAMPLE && action == ACTION_SKIP;  // rejected like any out-of-range action, but not an error
                 tl.live += skipped ? 0u : 1u;
@@ -653,7 +658,8 @@ struct WarpTile {
     // per warp: buffer | list E (u32: slot | control word << 8) | list S (u8 slot); the warps' mbarriers sit in the block header
     static constexpr size_t OFF_LIST_E = (BUF_BYTES + 15) / 16 * 16;
     static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 4;
-    static constexpr size_t WARP_BYTES = (OFF_LIST_S + (size_t)T + 127) / 128 * 128;
+    static constexpr size_t OFF_ACT = OFF_LIST_S + (size_t)T;  // u8 per slot: the caller's actions (pkb_step), fetched while the tile loads
+    static constexpr size_t WARP_BYTES = (OFF_ACT + (size_t)T + 127) / 128 * 128;
     static constexpr size_t HEADER = 128;
     static constexpr size_t BYTES = HEADER + WARP_BYTES * PKB_WT_WARPS;
     static constexpr int THREADS = 32 * PKB_WT_WARPS;
@@ -678,6 +684,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     const uint32_t bar = smem_u32(smem) + 8u * (uint32_t)warp, buf_s = smem_u32(buf);
     uint32_t* list_e = reinterpret_cast<uint32_t*>(buf + L::OFF_LIST_E);
     uint8_t* list_s = buf + L::OFF_LIST_S;
+    uint8_t* act_row = buf + L::OFF_ACT;
     View<T> v = tile_view<L>(buf);
     uint32_t* ep = reinterpret_cast<uint32_t*>(buf + L::OFF_EP);
     const uint32_t lanes_below = (1u << lane) - 1u;
@@ -718,6 +725,22 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         }
         uint32_t next = 0;
         if (lane == 0) next = atomicAdd(&d.sched[0], 1u);  // consumed after the stores
+        if (!SAMPLE) {  // the caller's actions, as bytes (254: out of range, 255: skip), fetched while the tile is in flight
+#pragma unroll
+            for (int k = 0; k < T / 32; ++k) {
+                const size_t env = base + (size_t)(lane + 32 * k);
+                uint32_t b = 254u;
+                if (env < d.n) {
+                    if (a.actions) {
+                        const int32_t x = a.actions[env];
+                        b = x == ACTION_SKIP ? 255u : (x < 0 || x > 253) ? 254u : (uint32_t)x;
+                    } else
+                        b = a.actions_u8[env];
+                }
+                act_row[lane + 32 * k] = (uint8_t)b;
+            }
+            __syncwarp();
+        }
         mbar_wait(bar, it & 1u);
         PKB_WTICK(0);
 
@@ -745,8 +768,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     const uint32_t word = shared_draw ? sample_word_of(draw, gid) : sample_word(a.gc.seed, gid, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     if (a.actions_out) a.actions_out[env] = action;
-                } else
-                    action = a.actions[env];
+                } else {
+                    action = act_row[s];
+                    action = action == 255 ? ACTION_SKIP : action;
+                }
                 step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
                 const bool skipped = !SAMPLE && action == ACTION_SKIP;  // rejected like any out-of-range action, but not an error
                 tl.live += skipped ? 0u : 1u;
@@ -1421,16 +1446,17 @@ int pkb_reset(pkb_env* h, const uint8_t* env_mask, void* stream)
 }
 
 static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_t* weights, const int32_t* actions,
-                       int32_t* actions_out, uint8_t* flags, uint8_t* valid, void* stream)
+                       const uint8_t* actions_u8, int32_t* actions_out, uint8_t* flags, uint8_t* valid, void* stream)
 {
     if (!h) return fail("pkb_step: null handle");
-    if (!sample && !actions) return fail("pkb_step: null actions");
+    if (!sample && !actions && !actions_u8) return fail("pkb_step: null actions");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     StepArgs a;
     a.maps = h->maps;
     a.d = h->d;
     a.gc = h->gc;
     a.actions = actions;
+    a.actions_u8 = actions_u8;
     a.actions_out = actions_out;
     a.flags = flags;
     a.valid = valid;
@@ -1448,13 +1474,18 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
 
 int pkb_step(pkb_env* h, const int32_t* actions, uint8_t* flags, uint8_t* valid, void* stream)
 {
-    return step_common(h, false, 0, nullptr, actions, nullptr, flags, valid, stream);
+    return step_common(h, false, 0, nullptr, actions, nullptr, nullptr, flags, valid, stream);
+}
+
+int pkb_step_u8(pkb_env* h, const uint8_t* actions, uint8_t* flags, uint8_t* valid, void* stream)
+{
+    return step_common(h, false, 0, nullptr, nullptr, actions, nullptr, flags, valid, stream);
 }
 
 int pkb_step_random(pkb_env* h, uint32_t step_idx, const uint32_t* weights, int32_t* actions_out, uint8_t* flags,
                     uint8_t* valid, void* stream)
 {
-    return step_common(h, true, step_idx, weights, nullptr, actions_out, flags, valid, stream);
+    return step_common(h, true, step_idx, weights, nullptr, nullptr, actions_out, flags, valid, stream);
 }
 
 int pkb_sample_actions(pkb_env* h, uint32_t step_idx, const uint32_t* weights, int32_t* actions_out, void* stream)

@@ -298,3 +298,34 @@ def test_scalar_facade_random_game(torch_cuda, ora):
     with pytest.raises((ValueError, IndexError)):
         game.step(7)
     assert np.array_equal(game.credits, before)
+
+
+@pytest.mark.gpu
+def test_step_u8_equals_step_i32():
+    """pkb_step_u8 (one byte per action, 255 = skip, anything else out of range = rejected) steps exactly like pkb_step."""
+    import torch
+    from pokerl_b200 import GameBatch
+    N, P = 3000, 3
+    a = GameBatch(N, P, 60, 2, 1, seed=5, auto_reset=True)
+    b = GameBatch(N, P, 60, 2, 1, seed=5, auto_reset=True)
+    a.reset(); b.reset()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for t in range(40):
+        acts = a.sample_actions(t).clone()
+        r = torch.rand(N, generator=g)
+        acts[(r < 0.1).to(acts.device)] = -2147483648          # skip
+        acts[((r >= 0.1) & (r < 0.15)).to(acts.device)] = 9     # out of range -> invalid
+        u8 = acts.clone()
+        u8[acts == -2147483648] = 255
+        fa, va = a.step(acts)
+        fb, vb = b.step(u8.to(torch.uint8))
+        assert torch.equal(fa, fb) and torch.equal(va, vb)
+    ea, eb = a.export(), b.export()
+    for k in ea:
+        assert np.array_equal(np.asarray(ea[k]).view(np.uint8), np.asarray(eb[k]).view(np.uint8)), k
+    sa, sb = a.stats(), b.stats()
+    for k in sa:  # the counters exactly; the payoff sums are float atomics accumulated in launch order
+        if k == "payoff_sum":
+            assert np.allclose(sa[k], sb[k], rtol=0, atol=1e-6)
+        else:
+            assert sa[k] == sb[k], k
