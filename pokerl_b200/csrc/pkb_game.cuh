@@ -54,17 +54,20 @@ struct View {
     PKB_HDM size_t ld() const { return LD ? (size_t)LD : ld_rt; }
 };
 
-// turn | dealer<<3 | small_blind_idx<<8 | big_blind_idx<<13 | active_player<<18
+// turn | dealer<<3 | small_blind_idx<<8 | big_blind_idx<<13 | active_player<<18 | valid<<23
+// `valid` caches get_valid_actions() of the active player (7 bits): every step ends by working it out for its outputs, and
+// the next step validates the action against it instead of recomputing it from the money planes.
 struct Meta {
     int turn, dealer, sb, bb, act;
+    uint32_t vm;
 };
 PKB_HD Meta unpack_meta(uint32_t w)
 {
-    return Meta{(int)(w & 7u), (int)(w >> 3 & 31u), (int)(w >> 8 & 31u), (int)(w >> 13 & 31u), (int)(w >> 18 & 31u)};
+    return Meta{(int)(w & 7u), (int)(w >> 3 & 31u), (int)(w >> 8 & 31u), (int)(w >> 13 & 31u), (int)(w >> 18 & 31u), w >> 23 & 127u};
 }
 PKB_HD uint32_t pack_meta(const Meta& m)
 {
-    return (uint32_t)m.turn | (uint32_t)m.dealer << 3 | (uint32_t)m.sb << 8 | (uint32_t)m.bb << 13 | (uint32_t)m.act << 18;
+    return (uint32_t)m.turn | (uint32_t)m.dealer << 3 | (uint32_t)m.sb << 8 | (uint32_t)m.bb << 13 | (uint32_t)m.act << 18 | m.vm << 23;
 }
 
 // ---- seat-state masks (enums.py:130-134: FOLDED 0, ACTIVE 1, CALLED 2, ALL_IN 3, BROKEN 4) -------

@@ -268,12 +268,16 @@ struct Tally {
 };
 
 // Step outputs of one finished env: flag bits and the valid mask of the new active player
+// (the valid mask is also cached in the meta word: the next step validates its action against it)
 template <int P, class V>
-PKB_D uint32_t write_outputs(const V& v, int s, const Ctl& c, const StepArgs& a, size_t env, bool skipped = false)
+PKB_D uint32_t write_outputs(V& v, int s, const Ctl& c, const StepArgs& a, size_t env, bool skipped = false)
 {
     const uint32_t f = skipped ? F_SKIPPED : (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
     if (a.flags) a.flags[env] = (uint8_t)f;
-    if (a.valid) a.valid[env] = (uint8_t)valid_mask<P>(v, s, unpack_meta(v.meta[s]).act);
+    const uint32_t w = v.meta[s];
+    const uint32_t vm = valid_mask<P>(v, s, unpack_meta(w).act);
+    v.meta[s] = (w & ~(127u << 23)) | vm << 23;
+    if (a.valid) a.valid[env] = (uint8_t)vm;
     return f;
 }
 
@@ -761,7 +765,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 Seats x = load_seats<P>(v, s);
                 Meta m = unpack_meta(v.meta[s]);
                 const double hb = high_bet<P>(v, s), credit = v.cr[m.act * T + s];
-                const uint32_t vm = valid_mask_from(hb, credit, v.mr[s]);
+                const uint32_t vm = m.vm;  // = valid_mask_from(hb, credit, v.mr[s]), left in the meta word by the previous step / reset
                 int action;
                 if (SAMPLE) {
                     const uint32_t gid = a.gc.env_id_base + (uint32_t)env;
@@ -945,6 +949,7 @@ __global__ void reset_kernel(DevState d, GameConst gc, const uint8_t* mask)
     Seats x{0, 0, 0, 0};
     reset_env<P>(v, env, x, m, gc);
     store_seats<P>(v, env, x);
+    m.vm = valid_mask<P>(v, env, m.act);
     d.meta[env] = pack_meta(m);
 }
 
