@@ -629,10 +629,13 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
 #define PKB_WT_MID 128    // P == 4
 #endif
 #ifndef PKB_WT_LARGE
-#define PKB_WT_LARGE 64   // P >= 5
+#define PKB_WT_LARGE 128  // P >= 5: list density beats warp count (measured: 128-env tiles, 6 warps/SM > 64-env tiles, 12 warps/SM)
 #endif
 #ifndef PKB_WT_WARPS
-#define PKB_WT_WARPS 4    // warps per block (they only share the block's statistics reduction)
+#define PKB_WT_WARPS 4    // warps per block (they only share the block's statistics reduction), P <= 4
+#endif
+#ifndef PKB_WT_WARPS_LARGE
+#define PKB_WT_WARPS_LARGE 2  // P >= 5
 #endif
 
 static_assert(STRIDE_ALIGN % PKB_WT_SMALL == 0 && STRIDE_ALIGN % PKB_WT_MID == 0 && STRIDE_ALIGN % PKB_WT_LARGE == 0, "warp tiles must divide the plane stride");
@@ -647,6 +650,7 @@ template <int P>
 struct WarpTile {
     static constexpr int T = wt_envs<P>();
     static constexpr int NP = P;
+    static constexpr int WARPS = P <= 4 ? PKB_WT_WARPS : PKB_WT_WARPS_LARGE;
     // one buffer = three dense row groups, each the box of one TMA descriptor (same row order as the HBM arena)
     static constexpr int F64_ROWS = 3 * P + 1;  // credits[P], bets[P], pending[P], minimum_raise
     static constexpr int U32_ROWS = 3;          // meta, hand, episode
@@ -665,13 +669,18 @@ struct WarpTile {
     static constexpr size_t OFF_ACT = OFF_LIST_S + (size_t)T;  // u8 per slot: the caller's actions (pkb_step), fetched while the tile loads
     static constexpr size_t WARP_BYTES = (OFF_ACT + (size_t)T + 127) / 128 * 128;
     static constexpr size_t HEADER = 128;
-    static constexpr size_t BYTES = HEADER + WARP_BYTES * PKB_WT_WARPS;
-    static constexpr int THREADS = 32 * PKB_WT_WARPS;
+    static constexpr size_t BYTES = HEADER + WARP_BYTES * WARPS;
+    static constexpr int THREADS = 32 * WARPS;
     // resident blocks per SM that 227 KB of shared memory (1 KB reserved per block) and 64 K registers at >= 64 per thread allow
     static constexpr int BY_SMEM = (int)((227 * 1024) / (BYTES + 1024));
     static constexpr int BY_REGS = 1024 / THREADS;
-    static constexpr int MIN_BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
-    static_assert(OFF_META % 128 == 0 && OFF_ST % 128 == 0 && PKB_WT_WARPS <= 16, "TMA box destinations are 128-byte aligned");
+    static constexpr int FIT_BLOCKS = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_REGS;
+#ifdef PKB_WT_BLOCKS  // tuning: cap the resident blocks per SM (more registers per thread, fewer warps)
+    static constexpr int MIN_BLOCKS = FIT_BLOCKS < PKB_WT_BLOCKS ? FIT_BLOCKS : PKB_WT_BLOCKS;
+#else
+    static constexpr int MIN_BLOCKS = FIT_BLOCKS;
+#endif
+    static_assert(OFF_META % 128 == 0 && OFF_ST % 128 == 0 && WARPS <= 16, "TMA box destinations are 128-byte aligned");
 };
 static_assert(PKB_WT_SMALL <= 256 && PKB_WT_MID <= 256 && PKB_WT_LARGE <= 256, "list entries hold the slot in 8 bits");
 
@@ -717,8 +726,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 #define PKB_WTICK(i)
 #endif
     // the first tile of a warp is its global index; further tiles come from a global dispenser, drawn one tile ahead
-    const uint32_t warps_total = gridDim.x * PKB_WT_WARPS;
-    uint32_t tile = blockIdx.x * PKB_WT_WARPS + warp;
+    const uint32_t warps_total = gridDim.x * L::WARPS;
+    uint32_t tile = blockIdx.x * L::WARPS + warp;
     for (uint32_t it = 0; tile < a.num_tiles; ++it) {
         const size_t base = (size_t)tile * T;
         if (lane == 0) {  // three TMA box copies bring the tile in
@@ -911,7 +920,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     if (lane == 0) bulk_wait_all();
 #ifdef PKB_TIMING
     {
-        const uint32_t gw = blockIdx.x * PKB_WT_WARPS + warp;
+        const uint32_t gw = blockIdx.x * L::WARPS + warp;
         if (lane == 0 && gw < 4096) {
             unsigned long long gt1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
@@ -1266,8 +1275,9 @@ static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_c
         fprintf(stderr, "pkb: step kernel P=%d warp tile=%d smem=%zu blocks/SM=%d (compiled for %d)\n", P, L::T, (size_t)L::BYTES,
                 blocks_per_sm[device], L::MIN_BLOCKS);
     a.num_tiles = (uint32_t)((a.d.n + L::T - 1) / L::T);
-    const unsigned resident = (unsigned)(blocks_per_sm[device] * sm_count);
-    const unsigned want = (a.num_tiles + PKB_WT_WARPS - 1) / PKB_WT_WARPS;
+    const int per_sm = blocks_per_sm[device] < L::MIN_BLOCKS ? blocks_per_sm[device] : L::MIN_BLOCKS;
+    const unsigned resident = (unsigned)(per_sm * sm_count);
+    const unsigned want = (a.num_tiles + L::WARPS - 1) / L::WARPS;
     step_warp_kernel<P, SAMPLE><<<want < resident ? want : resident, L::THREADS, L::BYTES, s>>>(a);
     return cudaGetLastError();
 }
