@@ -456,7 +456,8 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
         const uint64_t board = 1ull << id[0] | 1ull << id[1] | 1ull << id[2] | 1ull << id[3] | 1ull << id[4];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const uint32_t r = eval_mask52_sel(board | 1ull << id[5 + 2 * p] | 1ull << id[6 + 2 * p]);
+            // a real call: one copy of the evaluator keeps the kernel's hot code inside the instruction cache (measured)
+            const uint32_t r = eval_mask52_sel_call(board | 1ull << id[5 + 2 * p] | 1ull << id[6 + 2 * p]);
             rk[p] = (todo >> p & 1u) ? r : PACKED_NONE;
         }
     } else {
