@@ -143,6 +143,9 @@ PKB_D void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef PKB_MBAR_HINT_NS
+#define PKB_MBAR_HINT_NS 20000
+#endif
 PKB_D bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -153,7 +156,7 @@ PKB_D bool mbar_try_wait(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, P1;\n"
         "}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): do not spin on issue slots
+        : "r"(bar), "r"(parity), "r"((uint32_t)PKB_MBAR_HINT_NS)  // suspend-time hint (ns): do not spin on issue slots
         : "memory");
     return ok != 0;
 }
