@@ -118,6 +118,13 @@ PKB_HD int first_from(uint32_t mask, int idx)
     const uint32_t hi = mask >> idx << idx;
     return ffs32(hi ? hi : mask) - 1;
 }
+// the same for a table of P seats; heads-up tables need no bit search: seat idx if it is in the mask, else the other one
+template <int P>
+PKB_HD int first_from_p(uint32_t mask, int idx)
+{
+    if constexpr (P == 2) return (mask >> idx & 1u) ? idx : idx ^ 1;
+    else return first_from(mask, idx);
+}
 
 // numpy float64 add.reduce order (pairwise_sum): n < 8 left to right from 0.0; n >= 8 eight lanes,
 // combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail
@@ -152,6 +159,7 @@ PKB_HD int first_playing(const Seats& x, int idx)
 {
     if (idx >= P) idx -= P;
     const uint32_t alive = all_seats<P>() & ~x.broken;
+    if constexpr (P == 2) return ((alive >> idx & 1u) || !alive) ? idx : idx ^ 1;
     return alive ? first_from(alive, idx) : idx;  // argmax of all-False is 0
 }
 
@@ -323,6 +331,7 @@ PKB_D uint32_t pack_ctl(const Ctl& c)
 template <int P>
 PKB_D uint32_t cyclic_interval(int act, int cur)
 {
+    if constexpr (P == 2) return act == cur ? 1u << act : 3u;
     const uint32_t ge_act = all_seats<P>() & ~((1u << act) - 1u), le_cur = (2u << cur) - 1u;
     return act <= cur ? (ge_act & le_cur) : (ge_act | le_cur);
 }
@@ -387,7 +396,7 @@ PKB_D void seat_scan(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
             } while (!cand);
         }
     }
-    m.act = first_from(cand, m.act);
+    m.act = first_from_p<P>(cand, m.act);
 }
 
 // Game.step up to the first end_hand (game.py:648-699 and 597-605).  `vmask`, `hb`, `credit`: the
