@@ -637,6 +637,10 @@ __global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_
 #ifndef PKB_WT_WARPS
 #define PKB_WT_WARPS 4    // warps per block (they only share the block's statistics reduction), P <= 4
 #endif
+#ifndef PKB_WT_STATIC_ROUNDS
+#define PKB_WT_STATIC_ROUNDS 2  // a warp's first tiles are fixed (global warp index + k * warps); the dispenser serves the rest
+#endif
+static_assert(PKB_WT_STATIC_ROUNDS >= 1, "a warp's first tile is always its global index");
 #ifndef PKB_WT_WARPS_LARGE
 #define PKB_WT_WARPS_LARGE 2  // P >= 5
 #endif
@@ -739,8 +743,11 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             tma_load_2d(buf_s + (uint32_t)L::OFF_META, &a.maps.u32, (int)base, 0, bar);
             tma_load_2d(buf_s + (uint32_t)L::OFF_ST, &a.maps.u8, (int)base, 0, bar);
         }
-        uint32_t next = 0;
-        if (lane == 0) next = atomicAdd(&d.sched[0], 1u);  // consumed after the stores
+        // the tile after this one: fixed for the first rounds (no atomic: thousands of warps asking one counter at the same
+        // moment wait microseconds for the answer), from the dispenser afterwards; lane 0 holds it, consumed after the stores
+        uint32_t next = tile + warps_total;
+        if (it + 1 >= (uint32_t)PKB_WT_STATIC_ROUNDS && lane == 0)
+            next = (uint32_t)PKB_WT_STATIC_ROUNDS * warps_total + atomicAdd(&d.sched[0], 1u);
         if (!SAMPLE) {  // the caller's actions, as bytes (254: out of range, 255: skip), fetched while the tile is in flight
 #pragma unroll
             for (int k = 0; k < T / 32; ++k) {
@@ -817,8 +824,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 #ifndef PKB_WT_NO_PREFETCH
         // The next tile is known by now (the dispenser answered during pass A): start it on its way into L2, so
         // that the load after this tile's stores finds it there instead of waiting on HBM with the buffer empty.
-        if (lane == 0 && warps_total + next < a.num_tiles) {
-            const int nb = (int)((warps_total + next) * (uint32_t)T);
+        if (lane == 0 && next < a.num_tiles) {
+            const int nb = (int)(next * (uint32_t)T);
             tma_prefetch_2d(&a.maps.f64, nb, 0);
             tma_prefetch_2d(&a.maps.u32, nb, 0);
             tma_prefetch_2d(&a.maps.u8, nb, 0);
@@ -914,7 +921,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             bulk_wait_read();  // the buffer is about to be refilled
         }
         __syncwarp();
-        tile = warps_total + __shfl_sync(FULL, next, 0);
+        tile = __shfl_sync(FULL, next, 0);
         PKB_WTICK(4);
 #ifdef PKB_TIMING
         wt_acc[5] += 1;
