@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PKB_ABI_VERSION 1
+#define PKB_ABI_VERSION 2
 #define PKB_MAX_PLAYERS 10
 #define PKB_NUM_MOVES 7
 
@@ -81,8 +81,11 @@ typedef struct pkb_state_view {
     double *pending_bets;     /* Game.pending_bets            game.py:262 */
     double *payoffs;          /* Game.payoffs                 game.py:264 */
     double *minimum_raise_value; /* Game.minimum_raise_value  game.py:263 */
-    uint8_t *player_states;   /* Game.player_states [P][stride] game.py:259 */
-    uint32_t *meta;           /* turn | dealer<<3 | small_blind_idx<<8 | big_blind_idx<<13 | active_player<<18 */
+    uint64_t *seat_masks;     /* Game.player_states game.py:259 as seat bit masks, one word per env [stride]:
+                               * ACTIVE | CALLED<<16 | ALL_IN<<32 | BROKEN<<48, bit p of a field = seat p (FOLDED: in
+                               * none); pkb_player_states() gives one PlayerState value per seat */
+    uint32_t *meta;           /* turn | dealer<<3 | small_blind_idx<<8 | big_blind_idx<<13 | active_player<<18 |
+                               * valid<<23 (the active player's valid-move mask, cached by the step that produced it) */
     uint32_t *hand;           /* Game.hand                    game.py:255 */
     uint32_t *episode;        /* number of reset() calls seen by the env (Philox counter word) */
 } pkb_state_view;
@@ -130,6 +133,8 @@ int pkb_valid_actions(pkb_env *h, int32_t player, uint8_t *valid, void *stream);
 /* Game.game_over, game.py:316-320: device u8[N]. */
 int pkb_game_over(pkb_env *h, uint8_t *out, void *stream);
 int pkb_state(pkb_env *h, pkb_state_view *out);
+/* Game.player_states, game.py:259, one PlayerState value per seat: out = device u8[num_players][stride] */
+int pkb_player_states(pkb_env *h, uint8_t *out, void *stream);
 /* Current deal of every env, device u8 [5+2P][stride]: rows 0..4 board (game.py:278),
  * rows 5+2p, 6+2p hole cards of seat p (game.py:385-389); card values. */
 int pkb_cards(pkb_env *h, uint8_t *out, void *stream);

@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_PLAYERS = 10
 NUM_MOVES = 7
 
@@ -45,7 +45,7 @@ class PkbStateView(C.Structure):
         ("pending_bets", C.c_void_p),
         ("payoffs", C.c_void_p),
         ("minimum_raise_value", C.c_void_p),
-        ("player_states", C.c_void_p),
+        ("seat_masks", C.c_void_p),
         ("meta", C.c_void_p),
         ("hand", C.c_void_p),
         ("episode", C.c_void_p),
@@ -81,6 +81,7 @@ SYMBOLS = {
     "pkb_valid_actions": (C.c_int, [_vp, _i32, _vp, _vp]),
     "pkb_game_over": (C.c_int, [_vp, _vp, _vp]),
     "pkb_state": (C.c_int, [_vp, C.POINTER(PkbStateView)]),
+    "pkb_player_states": (C.c_int, [_vp, _vp, _vp]),
     "pkb_cards": (C.c_int, [_vp, _vp, _vp]),
     "pkb_hand_features": (C.c_int, [_vp, _i32, _vp, _vp]),
     "pkb_stats": (C.c_int, [_vp, C.POINTER(PkbStats), _vp]),

@@ -101,10 +101,20 @@ class GameBatch:
         self.pending_bets = wrap(sv.pending_bets, (P, S), "<f8")[:, :N]
         self.payoffs = wrap(sv.payoffs, (P, S), "<f8")[:, :N]
         self.minimum_raise_value = wrap(sv.minimum_raise_value, (S,), "<f8")[:N]
-        self.player_states = wrap(sv.player_states, (P, S), "|u1")[:, :N]
+        # player_states live on the device as four 16-bit seat masks per env (ACTIVE | CALLED<<16 | ALL_IN<<32 | BROKEN<<48)
+        self.seat_masks = wrap(sv.seat_masks, (S,), "<i8")[:N]
+        self._states_buf = None
         self._meta = wrap(sv.meta, (S,), "<i4")[:N]
         self._hand = wrap(sv.hand, (S,), "<i4")[:N]
         self._episode = wrap(sv.episode, (S,), "<i4")[:N]
+
+    @property
+    def player_states(self):
+        """Game.player_states (game.py:259) for every env: uint8 [P, N], one PlayerState value per seat (a fresh copy)."""
+        if self._states_buf is None:
+            self._states_buf = torch.zeros((self.num_players, self.stride), dtype=torch.uint8, device=self.device)
+        nat.check(nat.lib().pkb_player_states(self._h.ptr, nat.ptr(self._states_buf), self._stream()))
+        return self._states_buf[:, :self.num_envs]
 
     @property
     def turn(self):

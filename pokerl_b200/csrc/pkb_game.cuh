@@ -6,8 +6,8 @@
 // (game.py:370-371, 675-678), sums follow numpy's add.reduce order, and the winner scan keeps
 // the judger.py:148 behaviour.
 //
-// Representation: while an env is being processed its per-seat PlayerState bytes are held as four
-// disjoint bit masks in registers (struct Seats; FOLDED = in none of them), so every np.sum /
+// Representation: the per-seat PlayerState values are kept -- in HBM, in the tile and in registers -- as four
+// disjoint seat bit masks (struct Seats; FOLDED = in none of them), so every np.sum /
 // np.argmax / np.roll over player_states of the reference (game.py:320, 337, 421, 471, 567-572,
 // 598-599, 683) is a popcount / find-first-set instead of a loop over seats.  Money planes are
 // addressed through a View: element (seat p, slot s) of a plane is plane[p * ld + s]; the same
@@ -47,7 +47,7 @@ struct View {
     double* bt;      // bets             [P][ld]
     double* pd;      // pending_bets     [P][ld]
     double* mr;      // minimum_raise    [ld]
-    uint8_t* st;     // player_states    [P][ld]  (read/written only by load_seats / store_seats)
+    uint64_t* sm;    // player_states    [ld]     four 16-bit seat masks per env (read/written only by load_seats / store_seats)
     uint32_t* meta;  // packed indices   [ld]
     uint32_t* hand;  // hand counter     [ld]
     size_t ld_rt;
@@ -78,28 +78,26 @@ struct Seats {
 template <int P>
 PKB_HD constexpr uint32_t all_seats() { return (1u << P) - 1u; }
 
+// Storage form of player_states: ACTIVE | CALLED << 16 | ALL_IN << 32 | BROKEN << 48, bit p of a field = seat p
+// (pkb_player_states / GameBatch.player_states give the reference's one value per seat).
 template <int P, class V>
-PKB_D Seats load_seats(const V& v, size_t s)
+PKB_HD Seats load_seats(const V& v, size_t s)
 {
-    Seats x{0, 0, 0, 0};
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const uint32_t st = v.st[p * v.ld() + s];
-        x.active |= (uint32_t)(st == ST_ACTIVE) << p;
-        x.called |= (uint32_t)(st == ST_CALLED) << p;
-        x.allin |= (uint32_t)(st == ST_ALL_IN) << p;
-        x.broken |= (uint32_t)(st == ST_BROKEN) << p;
-    }
-    return x;
+    const uint64_t w = v.sm[s];
+    return Seats{(uint32_t)w & 0xffffu, (uint32_t)(w >> 16) & 0xffffu, (uint32_t)(w >> 32) & 0xffffu, (uint32_t)(w >> 48)};
 }
 
 template <int P, class V>
-PKB_D void store_seats(V& v, size_t s, const Seats& x)
+PKB_HD void store_seats(V& v, size_t s, const Seats& x)
 {
-#pragma unroll
-    for (int p = 0; p < P; ++p)
-        v.st[p * v.ld() + s] = (uint8_t)((x.active >> p & 1u) * ST_ACTIVE + (x.called >> p & 1u) * ST_CALLED +
-                                         (x.allin >> p & 1u) * ST_ALL_IN + (x.broken >> p & 1u) * ST_BROKEN);
+    v.sm[s] = (uint64_t)(x.active | x.called << 16) | (uint64_t)(x.allin | x.broken << 16) << 32;
+}
+
+// one seat's PlayerState value (enums.py:130-134) out of the masks
+PKB_HD uint32_t seat_state(const Seats& x, int p)
+{
+    return (x.active >> p & 1u) * ST_ACTIVE + (x.called >> p & 1u) * ST_CALLED + (x.allin >> p & 1u) * ST_ALL_IN +
+           (x.broken >> p & 1u) * ST_BROKEN;
 }
 
 // player_states[p] = state
@@ -253,9 +251,9 @@ template <int P>
 inline void fill_fresh_state(GameConst& gc)
 {
     double cr[P], bt[P], pd[P], mr[1] = {0.0};
-    uint8_t st[P];
+    uint64_t sm[1] = {0};
     uint32_t meta[1] = {0}, hand[1] = {0};
-    View<0> v{cr, bt, pd, mr, st, meta, hand, 1};
+    View<0> v{cr, bt, pd, mr, sm, meta, hand, 1};
     Seats x{0, 0, 0, 0};
     Meta m = unpack_meta(0);
     reset_env<P>(v, 0, x, m, gc);

@@ -1,9 +1,9 @@
 // pkb_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/pokerl_b200.h.
 //
 // Kernels
-//   step_tile_kernel K1+K2(+K5,K6) Game.step on tiles of envs held in shared memory: TMA bulk loads of the
-//                                SoA plane rows, three phases (every env / end_hand list / showdown
-//                                list) on block-compacted slot lists, TMA bulk stores
+//   step_warp_kernel K1+K2(+K5,K6) Game.step: a 128-env tile per warp held in shared memory (2-D TMA tensor copies of
+//                                the SoA plane rows), passes over warp-compacted slot lists (every env /
+//                                showdown list / end_hand list)
 //   reset_kernel     K3          Game.reset / setup_hand (dealing is a pure Philox function)
 //   eval_*_kernel    K4          eval_hand on card lists / id masks / all C(52,k) hands
 //   sample_kernel    K5          RandomAgent over the valid mask
@@ -27,7 +27,7 @@ namespace pkb {
 // --------------------------------------------------------------------------------------------
 struct DevState {
     double *cr, *bt, *pd, *mr, *payoffs;
-    uint8_t* st;
+    uint64_t* sm;  // seat masks (player_states), one 64-bit word per env: the row after mr
     uint32_t *meta, *hand, *episode;
     unsigned long long* stats;  // [STAT_COUNT] counters
     double* payoff_sum;         // [MAX_PLAYERS]
@@ -37,11 +37,10 @@ struct DevState {
 
 enum : int { STAT_STEPS = 0, STAT_HANDS, STAT_SHOWDOWNS, STAT_GAMES, STAT_INVALID, STAT_POISONED, STAT_COUNT };
 
-// TMA descriptors of the three plane groups of a handle (2-D: [rows][stride]), box = [rows][warp tile]
+// TMA descriptors of the two plane groups of a handle (2-D: [rows][stride]), box = [rows][warp tile]
 struct alignas(64) TileMaps {
-    CUtensorMap f64;  // credits, bets, pending_bets ([P] rows each) and minimum_raise_value: 3P + 1 rows of f64
+    CUtensorMap w64;  // credits, bets, pending_bets ([P] rows each), minimum_raise_value, seat masks: 3P + 2 rows of 8-byte words
     CUtensorMap u32;  // meta, hand, episode
-    CUtensorMap u8;   // player_states: P rows
 };
 
 struct StepArgs {
@@ -59,78 +58,12 @@ struct StepArgs {
     uint32_t num_tiles;
 };
 
-// ---- tuning knobs of the step kernel (defaults: the measured best on B200) ----
-#ifndef PKB_TILE_SMALL
-#define PKB_TILE_SMALL 512     // envs per tile for P <= 4
-#endif
-#ifndef PKB_TILE_LARGE
-#define PKB_TILE_LARGE 128     // envs per tile for P >= 5
-#endif
-#ifndef PKB_THREADS_SMALL
-#define PKB_THREADS_SMALL 256  // block size for P <= 4
-#endif
-#ifndef PKB_THREADS_LARGE
-#define PKB_THREADS_LARGE 128  // block size for P >= 5
-#endif
-#ifndef PKB_MIN_BLOCKS_SMALL
-#define PKB_MIN_BLOCKS_SMALL 3  // resident blocks per SM the kernel is compiled for (register cap), P <= 4
-#endif
-#ifndef PKB_MIN_BLOCKS_LARGE
-#define PKB_MIN_BLOCKS_LARGE 4  // the same for P >= 5
-#endif
 constexpr int STRIDE_ALIGN = 1024;  // env-count granularity of the HBM planes: a multiple of every tile size
-static_assert(STRIDE_ALIGN % PKB_TILE_SMALL == 0 && STRIDE_ALIGN % PKB_TILE_LARGE == 0, "tiles must divide the plane stride");
-
-// envs per tile: the tile (78 B per heads-up env, 278 B per ten-player env) stays well below 1/3 of
-// the 227 KB of shared memory so that three blocks are resident per SM
-template <int P>
-__host__ __device__ constexpr int step_threads()
-{
-    return P <= 4 ? PKB_THREADS_SMALL : PKB_THREADS_LARGE;
-}
-template <int P>
-__host__ __device__ constexpr int step_min_blocks()
-{
-    return P <= 4 ? PKB_MIN_BLOCKS_SMALL : PKB_MIN_BLOCKS_LARGE;
-}
-template <int P>
-__host__ __device__ constexpr int tile_envs()
-{
-    return P <= 4 ? PKB_TILE_SMALL : PKB_TILE_LARGE;
-}
 
 PKB_D View<0> global_view(const DevState& d)
 {
-    return View<0>{d.cr, d.bt, d.pd, d.mr, d.st, d.meta, d.hand, (size_t)d.stride};
+    return View<0>{d.cr, d.bt, d.pd, d.mr, d.sm, d.meta, d.hand, (size_t)d.stride};
 }
-
-// ---- shared-memory tile: [field][slot] rows in the same order and element types as the HBM
-// planes, so each row is ONE contiguous bulk copy in either direction.  A block holds NBUF such
-// buffers (the tile being stepped and the next one in flight) plus one set of work lists. -------------
-template <int P>
-struct Tile {
-    static constexpr int T = tile_envs<P>();
-    static constexpr int NP = P;
-    static constexpr int NBUF = 2;
-    static constexpr int ROWS = 4 * P + 3;       // rows stored back: 3P f64 seat rows, mr, meta, hand, P state rows
-    static constexpr int LOAD_ROWS = ROWS + 1;   // + the episode counters (read-only in the tile: the deal replay is keyed by them)
-    // offsets inside one buffer
-    static constexpr size_t OFF_CR = 0;
-    static constexpr size_t OFF_BT = OFF_CR + (size_t)P * T * 8;
-    static constexpr size_t OFF_PD = OFF_BT + (size_t)P * T * 8;
-    static constexpr size_t OFF_MR = OFF_PD + (size_t)P * T * 8;
-    static constexpr size_t OFF_META = OFF_MR + (size_t)T * 8;
-    static constexpr size_t OFF_HAND = OFF_META + (size_t)T * 4;
-    static constexpr size_t OFF_ST = OFF_HAND + (size_t)T * 4;
-    static constexpr size_t OFF_EP = (OFF_ST + (size_t)P * T + 15) / 16 * 16;  // u32 episode counters
-    static constexpr size_t BUF_BYTES = (OFF_EP + (size_t)T * 4 + 127) / 128 * 128;
-    // block layout: header (mbarriers, list counters) | NBUF buffers | ctl | list E | list S
-    static constexpr size_t HEADER = 128;
-    static constexpr size_t OFF_CTL = HEADER + NBUF * BUF_BYTES;      // u32 control word of parked slots
-    static constexpr size_t OFF_LIST_E = OFF_CTL + (size_t)T * 4;     // u16 slots whose hand ended
-    static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 2;  // u16 slots that need a ranked showdown
-    static constexpr size_t BYTES = OFF_LIST_S + (size_t)T * 2;
-};
 
 PKB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -167,18 +100,6 @@ PKB_D void mbar_wait(uint32_t bar, uint32_t parity)
     for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls)
         if (polls > (1u << 18)) __trap();
 }
-// TMA 1-D bulk copies (SASS: UBLKCP); sizes and addresses are multiples of 16 bytes
-PKB_D void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-PKB_D void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
-                 : "memory");
-}
 // TMA 2-D tiled copies (SASS: UTMALDG / UTMASTG): box [rows][tile envs] <-> dense shared-memory rows
 PKB_D void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar)
 {
@@ -201,41 +122,6 @@ PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::
 PKB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 PKB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// row r of a tile: where it lives in HBM (for the tile that starts at env `base`) and inside a tile buffer
-template <class L>
-PKB_D void tile_row(const DevState& d, size_t base, int r, char*& gptr, uint32_t& soff, uint32_t& bytes)
-{
-    constexpr int T = L::T, P = L::NP;
-    if (r < 3 * P) {
-        const int plane = r / P, seat = r - plane * P;
-        double* g = plane == 0 ? d.cr : plane == 1 ? d.bt : d.pd;
-        gptr = reinterpret_cast<char*>(g + (size_t)seat * d.stride + base);
-        soff = (uint32_t)(L::OFF_CR + (size_t)r * T * 8);
-        bytes = T * 8;
-    } else if (r == 3 * P) {
-        gptr = reinterpret_cast<char*>(d.mr + base);
-        soff = (uint32_t)L::OFF_MR;
-        bytes = T * 8;
-    } else if (r == 3 * P + 1) {
-        gptr = reinterpret_cast<char*>(d.meta + base);
-        soff = (uint32_t)L::OFF_META;
-        bytes = T * 4;
-    } else if (r == 3 * P + 2) {
-        gptr = reinterpret_cast<char*>(d.hand + base);
-        soff = (uint32_t)L::OFF_HAND;
-        bytes = T * 4;
-    } else if (r < L::ROWS) {
-        const int seat = r - (3 * P + 3);
-        gptr = reinterpret_cast<char*>(d.st + (size_t)seat * d.stride + base);
-        soff = (uint32_t)(L::OFF_ST + (size_t)seat * T);
-        bytes = T;
-    } else {
-        gptr = reinterpret_cast<char*>(d.episode + base);
-        soff = (uint32_t)L::OFF_EP;
-        bytes = T * 4;
-    }
-}
-
 template <class L>
 PKB_D View<L::T> tile_view(unsigned char* smem)
 {
@@ -246,21 +132,9 @@ PKB_D View<L::T> tile_view(unsigned char* smem)
     v.mr = reinterpret_cast<double*>(smem + L::OFF_MR);
     v.meta = reinterpret_cast<uint32_t*>(smem + L::OFF_META);
     v.hand = reinterpret_cast<uint32_t*>(smem + L::OFF_HAND);
-    v.st = smem + L::OFF_ST;
+    v.sm = reinterpret_cast<uint64_t*>(smem + L::OFF_SM);
     v.ld_rt = L::T;
     return v;
-}
-
-// warp-aggregated append of a slot to a block-local work list (shared-memory counter)
-PKB_D void list_append(uint16_t* list, uint32_t* counter, bool mine, uint32_t slot)
-{
-    const unsigned vote = __ballot_sync(__activemask(), mine);
-    if (!mine) return;
-    const int lane = threadIdx.x & 31, leader = __ffs((int)vote) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(vote));
-    base = __shfl_sync(vote, base, leader);
-    list[base + (uint32_t)__popc(vote & ((1u << lane) - 1u))] = (uint16_t)slot;
 }
 
 // per-thread statistics of one launch, reduced once per block
@@ -313,308 +187,9 @@ PKB_D void reduce_stats(const DevState& d, const Tally<P>& tl)
     if (tid >= 32 && tid < 32 + P && s_pay[tid - 32] != 0.0) atomicAdd(&d.payoff_sum[tid - 32], s_pay[tid - 32]);
 }
 
-// --------------------------------------------------------------------------------------------
-// Game.step (game.py:621-700) on every env: ONE persistent kernel.
-//
-// A block walks tiles of T envs.  A tile's plane rows are pulled into a shared-memory buffer by TMA
-// bulk copies (the next tile is prefetched into the other buffer while this one is stepped), stepped
-// in place, and pushed back by TMA bulk copies, so each env's state crosses HBM exactly once in each
-// direction per step.
-//
-// The branches of a step differ by 10-100x in cost (a bet; a hand that ends: ~1/3 of heads-up steps;
-// a ranked showdown: ~1/8), and with 32 envs per warp every warp would execute all of them.  So the
-// work is split into three passes over the tile that hand the expensive cases on through compacted
-// slot lists, each pass running at full warp width:
-//   A  every slot:       validate/sample the action, bet, seat scan, next_turn commits; when the hand
-//                        ends also end_hand's head (commit, last-stand pot)       -> list E (+ list S)
-//   C  slots in list S:  the ranked showdown (deal replay, 7-card ranks, side pots)
-//   D  slots in list E:  end_hand's tail (payoffs, BROKEN seats, auto-reset, next hand's blinds), the
-//                        resumed seat scan and the step's outputs
-// --------------------------------------------------------------------------------------------
 #ifdef PKB_TIMING
-__device__ unsigned long long g_span[3] = {~0ull, 0ull, 0ull};  // globaltimer: earliest block start, latest block start, latest block end
-__device__ unsigned long long g_blk[2048][4];  // per block of the last launch: start ns, end ns, SM id, tiles
-__device__ unsigned long long g_wrp[4096][12];  // per warp of the last warp-tile launch: start ns, end ns, SM id, 5 phase cycle sums, tiles
-__device__ unsigned long long g_timing[8];  // cycles as seen by thread 0: load wait, A, C, D, store issue, whole block, tiles
-#define PKB_TICK(i)                                        \
-    do {                                                   \
-        if (tid == 0) {                                    \
-            const long long now_ = clock64();              \
-            tacc[i] += (unsigned long long)(now_ - tlast); \
-            tlast = now_;                                  \
-        }                                                  \
-    } while (0)
-#else
-#define PKB_TICK(i)
+__device__ unsigned long long g_wrp[4096][12];  // per warp of the last launch: start ns, end ns, SM id, 5 phase cycle sums, tiles, C/D rounds, longest C pass, max showdowns
 #endif
-
-// The rare rest of a step in which ANOTHER hand ends (all-in blinds): whole hands, one after the
-// other, until the step is done.  Out of line: it is a second copy of passes A-tail, C and D.
-template <int P>
-__device__ __noinline__ void run_further_hands(unsigned char* buf, uint32_t* ctl, const uint32_t* ep, int s, size_t env,
-                                               const StepArgs& a)
-{
-    using L = Tile<P>;
-    View<L::T> v = tile_view<L>(buf);
-    const DevState& d = a.d;
-    Seats x = load_seats<P>(v, s);
-    Ctl c = unpack_ctl(ctl[s]);
-    Meta m = unpack_meta(v.meta[s]);
-    uint32_t episode = ep[s];
-    unsigned long long hands = 0, shows = 0;
-    while (c.pc == PC_END_HAND) {
-        ++hands;
-        const bool ranked = end_hand_begin<P>(v, s, x, c);
-        if (!ranked && c.poisoned) break;
-        if (ranked) {
-            ++shows;
-            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)env, episode);
-        }
-        c.pc = PC_DONE;
-        double pay[P];
-        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) d.episode[env] = ++episode;
-        if (a.gc.track_stats)
-            for (int p = 0; p < P; ++p) atomicAdd(&d.payoff_sum[p], pay[p]);
-    }
-    if (a.gc.track_stats) {
-        atomicAdd(&d.stats[STAT_HANDS], hands);
-        atomicAdd(&d.stats[STAT_SHOWDOWNS], shows);
-    }
-    store_seats<P>(v, s, x);
-    v.meta[s] = pack_meta(m);
-    ctl[s] = pack_ctl(c);
-}
-
-template <int P, bool SAMPLE>
-__global__ void __launch_bounds__(step_threads<P>(), step_min_blocks<P>()) step_tile_kernel(const __grid_constant__ StepArgs a)
-{
-    using L = Tile<P>;
-    constexpr int T = L::T, NBUF = L::NBUF, STEP_THREADS = step_threads<P>();
-    static_assert(T % STEP_THREADS == 0 && L::LOAD_ROWS <= STEP_THREADS, "tile / block shape");
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + L::OFF_CTL);
-    uint16_t* list_e = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST_E);
-    uint16_t* list_s = reinterpret_cast<uint16_t*>(smem + L::OFF_LIST_S);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + 8 * NBUF);  // list lengths {E, S}
-    const uint32_t smem_base = smem_u32(smem);
-    const DevState& d = a.d;
-    const int tid = threadIdx.x;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int b = 0; b < NBUF; ++b) mbar_init(smem_base + 8 * b, L::LOAD_ROWS);
-        cnt[0] = cnt[1] = 0;
-    }
-    __syncthreads();
-
-    // thread r owns row r of every tile, in both directions
-    auto issue_load = [&](uint32_t tile, int b) {
-        if (tid < L::LOAD_ROWS) {
-            char* g;
-            uint32_t soff, bytes;
-            tile_row<L>(d, (size_t)tile * T, tid, g, soff, bytes);
-            bulk_wait_read();  // this row's last store has left shared memory
-            mbar_arrive_expect_tx(smem_base + 8 * b, bytes);
-            bulk_load(smem_base + (uint32_t)(L::HEADER + b * L::BUF_BYTES) + soff, g, bytes, smem_base + 8 * b);
-        }
-    };
-
-    Tally<P> tl;
-#pragma unroll
-    for (int p = 0; p < P; ++p) tl.pay[p] = 0.0;
-    tl.hands = tl.shows = tl.games = tl.poisoned = tl.invalid = tl.live = 0;
-#ifdef PKB_TIMING
-    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tlast = clock64();
-    const long long tstart = tlast;
-    unsigned long long gt0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
-#endif
-
-    // tiles are handed out dynamically (one global atomic per tile): blocks that drew cheap tiles take more
-    uint32_t* next_tile = reinterpret_cast<uint32_t*>(smem + 8 * NBUF + 8);  // [2], written by thread 0
-    if (tid == 0) next_tile[0] = atomicAdd(&d.sched[0], 1u);
-    __syncthreads();
-    uint32_t tile = next_tile[0];
-    if (tile < a.num_tiles) issue_load(tile, 0);
-    for (uint32_t it = 0; tile < a.num_tiles; ++it) {
-        const int b = (int)(it % NBUF);
-        unsigned char* buf = smem + L::HEADER + b * L::BUF_BYTES;
-        View<T> v = tile_view<L>(buf);
-        const uint32_t* ep = reinterpret_cast<const uint32_t*>(buf + L::OFF_EP);
-        const size_t base = (size_t)tile * T;
-        if (tid == 0) next_tile[(it + 1) & 1] = atomicAdd(&d.sched[0], 1u);  // read by everyone after pass A's barrier
-        mbar_wait(smem_base + 8 * b, (it / NBUF) & 1u);
-        PKB_TICK(0);
-
-        // ---- pass A: every slot (one copy of the body: the hot loop has to stay in the instruction cache)
-#pragma unroll 1
-        for (int s = tid; s < T; s += STEP_THREADS) {
-            const size_t env = base + s;
-            const bool live = env < d.n;
-            Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
-            if (live) {
-                Seats x = load_seats<P>(v, s);
-                Meta m = unpack_meta(v.meta[s]);
-                const double hb = high_bet<P>(v, s), credit = v.cr[m.act * T + s];
-                const uint32_t vm = valid_mask_from(hb, credit, v.mr[s]);
-                int action;
-                if (SAMPLE) {
-                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
-                    action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
-                    if (a.actions_out) a.actions_out[env] = action;
-                } else if (a.actions)
-                    action = a.actions[env];
-                else {
-                    action = a.actions_u8[env];
-                    action = action == 255 ? ACTION_SKIP : action;
-                }
-                step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
-                const bool skipped = !SAMPLE && action == ACTION_SKIP;  // rejected like any out-of-range action, but not an error
-                tl.live += skipped ? 0u : 1u;
-                tl.invalid += skipped ? 0u : (uint32_t)c.invalid;
-                if (c.pc == PC_END_HAND) {
-                    // end_hand's head (game.py:453-482) right here: it is short, and it decides the list
-                    ++tl.hands;
-                    if (end_hand_begin<P>(v, s, x, c)) c.pc = PC_SHOWDOWN;
-                    ctl[s] = pack_ctl(c);
-                }
-                if (!c.invalid) {  // an invalid action changes nothing (game.py:649-651)
-                    store_seats<P>(v, s, x);
-                    v.meta[s] = pack_meta(m);
-                }
-                if (c.pc == PC_DONE) {
-                    tl.poisoned += (uint32_t)c.poisoned;
-                    write_outputs<P>(v, s, c, a, env, skipped);
-                }
-            }
-            list_append(list_e, &cnt[0], live && c.pc != PC_DONE, (uint32_t)s);
-            list_append(list_s, &cnt[1], live && c.pc == PC_SHOWDOWN, (uint32_t)s);
-        }
-        __syncthreads();
-        PKB_TICK(1);
-        // the other buffer is free (its stores were issued before pass A): prefetch the next tile into it
-        const uint32_t tile_after = next_tile[(it + 1) & 1];
-        if (tile_after < a.num_tiles) issue_load(tile_after, b ^ 1);
-
-        // both list lengths are read here, so that thread 0 can clear the counters after the next barrier
-#if defined(PKB_DEBUG_SKIP)
-        const uint32_t n_s = 0;  // timing experiment only: results are wrong
-#else
-        const uint32_t n_s = cnt[1];
-#endif
-#if defined(PKB_DEBUG_SKIP) && PKB_DEBUG_SKIP == 1
-        const uint32_t n_e = 0;  // timing experiment only: results are wrong
-#else
-        const uint32_t n_e = cnt[0];
-#endif
-
-        // ---- pass C: the ranked showdown for the slots in list S
-        for (uint32_t i = tid; i < n_s; i += STEP_THREADS) {
-            const int s = list_s[i];
-            const Seats x = load_seats<P>(v, s);
-            const Ctl c = unpack_ctl(ctl[s]);
-            ++tl.shows;
-            showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
-        }
-        __syncthreads();
-        PKB_TICK(2);
-        if (tid == 0) cnt[0] = cnt[1] = 0;  // every thread has read them; the next pass A is two barriers away
-
-        // ---- pass D: the rest of end_hand and of the step for the slots in list E
-        for (uint32_t i = tid; i < n_e; i += STEP_THREADS) {
-            const int s = list_e[i];
-            const size_t env = base + s;
-            Seats x = load_seats<P>(v, s);
-            Ctl c = unpack_ctl(ctl[s]);
-            Meta m = unpack_meta(v.meta[s]);
-            if (c.poisoned) {
-                // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
-                // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED
-#pragma unroll
-                for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
-                c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
-                c.pc = PC_DONE;
-            } else {
-                c.pc = PC_DONE;
-                double pay[P];
-                if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) d.episode[env] = ep[s] + 1;
-#pragma unroll
-                for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
-                store_seats<P>(v, s, x);
-                v.meta[s] = pack_meta(m);
-                if (c.pc == PC_END_HAND) {  // another hand ends inside this step
-                    ctl[s] = pack_ctl(c);
-                    run_further_hands<P>(buf, ctl, ep, s, env, a);
-                    c = unpack_ctl(ctl[s]);
-                    if (c.poisoned) {
-#pragma unroll
-                        for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
-                        x = load_seats<P>(v, s);
-                        c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
-                        c.pc = PC_DONE;
-                    }
-                }
-            }
-            const uint32_t f = write_outputs<P>(v, s, c, a, env);
-            tl.games += (f & F_GAME_OVER) ? 1u : 0u;
-            tl.poisoned += (uint32_t)c.poisoned;
-        }
-
-        // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
-        fence_async_smem();
-        __syncthreads();
-        PKB_TICK(3);
-#ifdef PKB_PLAIN_STORE
-        for (int r = 0; r < L::ROWS; ++r) {  // experiment: plain 128-bit coalesced stores instead of TMA
-            char* g;
-            uint32_t soff, bytes;
-            tile_row<L>(d, base, r, g, soff, bytes);
-            for (uint32_t o = tid * 16; o < bytes; o += STEP_THREADS * 16)
-                *reinterpret_cast<uint4*>(g + o) = *reinterpret_cast<const uint4*>(buf + soff + o);
-        }
-#else
-        if (tid < L::ROWS) {
-            char* g;
-            uint32_t soff, bytes;
-            tile_row<L>(d, base, tid, g, soff, bytes);
-            bulk_store(g, smem_base + (uint32_t)(L::HEADER + b * L::BUF_BYTES) + soff, bytes);
-            bulk_commit();
-        }
-#endif
-        PKB_TICK(4);
-#ifdef PKB_TIMING
-        if (tid == 0) tacc[6] += 1;
-#endif
-        tile = tile_after;
-    }
-    if (tid < L::ROWS) bulk_wait_all();
-    if (tid == 0 && atomicAdd(&d.sched[1], 1u) == gridDim.x - 1) {  // the last block to finish re-arms the scheduler
-        d.sched[0] = 0;
-        d.sched[1] = 0;
-    }
-#ifdef PKB_TIMING
-    if (tid == 0) {
-        tacc[5] = (unsigned long long)(clock64() - tstart);
-        unsigned long long gt1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
-        for (int i = 0; i < 7; ++i) atomicAdd(&g_timing[i], tacc[i]);
-        atomicAdd(&g_timing[7], gt1 - gt0);  // nanoseconds
-        if (blockIdx.x < 2048) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_blk[blockIdx.x][0] = gt0;
-            g_blk[blockIdx.x][1] = gt1;
-            g_blk[blockIdx.x][2] = smid;
-            g_blk[blockIdx.x][3] = tacc[6];
-        }
-        atomicMin(&g_span[0], gt0);
-        atomicMax(&g_span[1], gt0);
-        atomicMax(&g_span[2], gt1);
-    }
-#endif
-    if (a.gc.track_stats) reduce_stats<P>(d, tl);
-}
 
 // --------------------------------------------------------------------------------------------
 // Game.step on every env, warp-tile form (the default): the same three passes, but a tile belongs to
@@ -658,18 +233,18 @@ struct WarpTile {
     static constexpr int T = wt_envs<P>();
     static constexpr int NP = P;
     static constexpr int WARPS = P <= 4 ? PKB_WT_WARPS : PKB_WT_WARPS_LARGE;
-    // one buffer = three dense row groups, each the box of one TMA descriptor (same row order as the HBM arena)
-    static constexpr int F64_ROWS = 3 * P + 1;  // credits[P], bets[P], pending[P], minimum_raise
+    // one buffer = two dense row groups, each the box of one TMA descriptor (same row order as the HBM arena)
+    static constexpr int W64_ROWS = 3 * P + 2;  // credits[P], bets[P], pending[P], minimum_raise, seat masks
     static constexpr int U32_ROWS = 3;          // meta, hand, episode
     static constexpr size_t OFF_CR = 0;
     static constexpr size_t OFF_BT = OFF_CR + (size_t)P * T * 8;
     static constexpr size_t OFF_PD = OFF_BT + (size_t)P * T * 8;
     static constexpr size_t OFF_MR = OFF_PD + (size_t)P * T * 8;
-    static constexpr size_t OFF_META = OFF_MR + (size_t)T * 8;
+    static constexpr size_t OFF_SM = OFF_MR + (size_t)T * 8;
+    static constexpr size_t OFF_META = OFF_SM + (size_t)T * 8;
     static constexpr size_t OFF_HAND = OFF_META + (size_t)T * 4;
     static constexpr size_t OFF_EP = OFF_HAND + (size_t)T * 4;
-    static constexpr size_t OFF_ST = OFF_EP + (size_t)T * 4;
-    static constexpr size_t BUF_BYTES = OFF_ST + (size_t)P * T;  // = bytes of the three boxes
+    static constexpr size_t BUF_BYTES = OFF_EP + (size_t)T * 4;  // = bytes of the two boxes
     // per warp: buffer | list E (u32: slot | control word << 8) | list S (u8 slot); the warps' mbarriers sit in the block header
     static constexpr size_t OFF_LIST_E = (BUF_BYTES + 15) / 16 * 16;
     static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 4;
@@ -687,7 +262,7 @@ struct WarpTile {
 #else
     static constexpr int MIN_BLOCKS = FIT_BLOCKS;
 #endif
-    static_assert(OFF_META % 128 == 0 && OFF_ST % 128 == 0 && WARPS <= 16, "TMA box destinations are 128-byte aligned");
+    static_assert(OFF_META % 128 == 0 && WARPS <= 16, "TMA box destinations are 128-byte aligned");
 };
 static_assert(PKB_WT_SMALL <= 256 && PKB_WT_MID <= 256 && PKB_WT_LARGE <= 256, "list entries hold the slot in 8 bits");
 
@@ -737,11 +312,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     uint32_t tile = blockIdx.x * L::WARPS + warp;
     for (uint32_t it = 0; tile < a.num_tiles; ++it) {
         const size_t base = (size_t)tile * T;
-        if (lane == 0) {  // three TMA box copies bring the tile in
+        if (lane == 0) {  // two TMA box copies bring the tile in
             mbar_arrive_expect_tx(bar, (uint32_t)L::BUF_BYTES);
-            tma_load_2d(buf_s + (uint32_t)L::OFF_CR, &a.maps.f64, (int)base, 0, bar);
+            tma_load_2d(buf_s + (uint32_t)L::OFF_CR, &a.maps.w64, (int)base, 0, bar);
             tma_load_2d(buf_s + (uint32_t)L::OFF_META, &a.maps.u32, (int)base, 0, bar);
-            tma_load_2d(buf_s + (uint32_t)L::OFF_ST, &a.maps.u8, (int)base, 0, bar);
         }
         // the tile after this one: fixed for the first rounds (no atomic: thousands of warps asking one counter at the same
         // moment wait microseconds for the answer), from the dispenser afterwards; lane 0 holds it, consumed after the stores
@@ -826,9 +400,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // that the load after this tile's stores finds it there instead of waiting on HBM with the buffer empty.
         if (lane == 0 && next < a.num_tiles) {
             const int nb = (int)(next * (uint32_t)T);
-            tma_prefetch_2d(&a.maps.f64, nb, 0);
+            tma_prefetch_2d(&a.maps.w64, nb, 0);
             tma_prefetch_2d(&a.maps.u32, nb, 0);
-            tma_prefetch_2d(&a.maps.u8, nb, 0);
         }
 #endif
 
@@ -914,9 +487,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         __syncwarp();
         PKB_WTICK(3);
         if (lane == 0) {
-            tma_store_2d(&a.maps.f64, (int)base, 0, buf_s + (uint32_t)L::OFF_CR);
+            tma_store_2d(&a.maps.w64, (int)base, 0, buf_s + (uint32_t)L::OFF_CR);
             tma_store_2d(&a.maps.u32, (int)base, 0, buf_s + (uint32_t)L::OFF_META);
-            tma_store_2d(&a.maps.u8, (int)base, 0, buf_s + (uint32_t)L::OFF_ST);
             bulk_commit();
             bulk_wait_read();  // the buffer is about to be refilled
         }
@@ -988,6 +560,17 @@ __global__ void game_over_kernel(DevState d, uint8_t* out)
     const size_t env = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= d.n) return;
     out[env] = game_over<P>(load_seats<P>(global_view(d), env)) ? 1 : 0;
+}
+
+// Game.player_states (game.py:259) in the reference's form, one PlayerState value per seat: out[p * stride + env]
+template <int P>
+__global__ void player_states_kernel(DevState d, uint8_t* out)
+{
+    const size_t env = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n) return;
+    const Seats x = load_seats<P>(global_view(d), env);
+#pragma unroll
+    for (int p = 0; p < P; ++p) out[(size_t)p * d.stride + env] = (uint8_t)seat_state(x, p);
 }
 
 // K5: RandomAgent (agents/random.py:16-17) / weighted mix over the valid mask
@@ -1257,26 +840,9 @@ static cudaError_t resident_blocks(K kernel, int threads, size_t smem, int devic
     return cudaSuccess;
 }
 
-// block-tile form (step_tile_kernel), kept for comparison: PKB_STEP_IMPL=tile
-template <int P, bool SAMPLE>
-static cudaError_t launch_step_tile(StepArgs& a, cudaStream_t s, int device, int sm_count)
-{
-    constexpr size_t smem = Tile<P>::BYTES;
-    static int blocks_per_sm[64] = {0};
-    cudaError_t e = resident_blocks(step_tile_kernel<P, SAMPLE>, step_threads<P>(), smem, device, blocks_per_sm);
-    if (e != cudaSuccess) return e;
-    a.num_tiles = (uint32_t)((a.d.n + tile_envs<P>() - 1) / tile_envs<P>());
-    const unsigned resident = (unsigned)(blocks_per_sm[device] * sm_count);
-    const unsigned grid = a.num_tiles < resident ? a.num_tiles : resident;
-    step_tile_kernel<P, SAMPLE><<<grid, step_threads<P>(), smem, s>>>(a);
-    return cudaGetLastError();
-}
-
 template <int P, bool SAMPLE>
 static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_count)
 {
-    static const bool use_tile = getenv("PKB_STEP_IMPL") && !strcmp(getenv("PKB_STEP_IMPL"), "tile");
-    if (use_tile) return launch_step_tile<P, SAMPLE>(a, s, device, sm_count);
     using L = WarpTile<P>;
     static int blocks_per_sm[64] = {0};
     cudaError_t e = resident_blocks(step_warp_kernel<P, SAMPLE>, L::THREADS, L::BYTES, device, blocks_per_sm);
@@ -1326,29 +892,15 @@ template <int P>
 static bool make_tile_maps(TileMaps& maps, const DevState& d)
 {
     using L = WarpTile<P>;
-    return make_plane_map(&maps.f64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, d.cr, d.stride, L::F64_ROWS, L::T) &&
-           make_plane_map(&maps.u32, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, d.meta, d.stride, L::U32_ROWS, L::T) &&
-           make_plane_map(&maps.u8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d.st, d.stride, P, L::T);
+    return make_plane_map(&maps.w64, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, d.cr, d.stride, L::W64_ROWS, L::T) &&
+           make_plane_map(&maps.u32, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, d.meta, d.stride, L::U32_ROWS, L::T);
 }
 
 extern "C" {
 
 #ifdef PKB_TIMING
-// debug builds only: read and clear the phase cycle counters of the step kernel
-int pkb_debug_timing(unsigned long long* out)
-{
-    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemcpyFromSymbol(out, g_timing, sizeof zero) != cudaSuccess) return -1;
-    return cudaMemcpyToSymbol(g_timing, zero, sizeof zero) == cudaSuccess ? 0 : -1;
-}
+// debug builds only: the per-warp timeline of the last step launch (profiles/warp_timing.py)
 int pkb_debug_warps(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_wrp, sizeof(unsigned long long) * 4096 * 12) == cudaSuccess ? 0 : -1; }
-int pkb_debug_blocks(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_blk, sizeof(unsigned long long) * 2048 * 4) == cudaSuccess ? 0 : -1; }
-int pkb_debug_span(unsigned long long* out)
-{
-    const unsigned long long init[3] = {~0ull, 0ull, 0ull};
-    if (cudaMemcpyFromSymbol(out, g_span, sizeof init) != cudaSuccess) return -1;
-    return cudaMemcpyToSymbol(g_span, init, sizeof init) == cudaSuccess ? 0 : -1;
-}
 #endif
 
 const char* pkb_last_error(void) { return g_error.c_str(); }
@@ -1379,9 +931,9 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     h->cfg = *cfg;
     const int P = cfg->num_players;
     const uint64_t n = cfg->num_envs, stride = (n + STRIDE_ALIGN - 1) / STRIDE_ALIGN * STRIDE_ALIGN;
-    // arena: f64 planes | u32 planes | u8 planes | stats
-    const size_t n_f64 = (size_t)(4 * P + 1) * stride, n_u32 = (size_t)3 * stride, n_u8 = (size_t)P * stride;
-    const size_t off_u32 = n_f64 * 8, off_u8 = off_u32 + n_u32 * 4, off_stats = (off_u8 + n_u8 + 255) / 256 * 256;
+    // arena: 8-byte planes (f64 money, seat masks) | u32 planes | stats
+    const size_t n_w64 = (size_t)(4 * P + 2) * stride, n_u32 = (size_t)3 * stride;
+    const size_t off_u32 = n_w64 * 8, off_stats = (off_u32 + n_u32 * 4 + 255) / 256 * 256;
     h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 2 * 4;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) {
@@ -1400,13 +952,13 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     d.cr = f;
     d.bt = f + (size_t)P * stride;
     d.pd = f + (size_t)2 * P * stride;
-    d.mr = f + (size_t)3 * P * stride;  // right after pending_bets: credits..minimum_raise are one 2-D TMA tensor of 3P+1 rows
-    d.payoffs = f + (size_t)(3 * P + 1) * stride;
+    d.mr = f + (size_t)3 * P * stride;  // right after pending_bets: credits .. seat masks are one 2-D TMA tensor of 3P+2 rows
+    d.sm = reinterpret_cast<uint64_t*>(f + (size_t)(3 * P + 1) * stride);
+    d.payoffs = f + (size_t)(3 * P + 2) * stride;
     uint32_t* u = reinterpret_cast<uint32_t*>(base + off_u32);
     d.meta = u;
     d.hand = u + stride;
     d.episode = u + 2 * stride;
-    d.st = reinterpret_cast<uint8_t*>(base + off_u8);
     d.stats = reinterpret_cast<unsigned long long*>(base + off_stats);
     d.payoff_sum = reinterpret_cast<double*>(base + off_stats + STAT_COUNT * 8);
     h->d_weights = reinterpret_cast<uint32_t*>(base + off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8);
@@ -1546,6 +1098,16 @@ int pkb_game_over(pkb_env* h, uint8_t* out, void* stream)
     return 0;
 }
 
+int pkb_player_states(pkb_env* h, uint8_t* out, void* stream)
+{
+    if (!h || !out) return fail("pkb_player_states: null argument");
+    PKB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_DISPATCH_P(h->cfg.num_players, (player_states_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, out)));
+    PKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int pkb_state(pkb_env* h, pkb_state_view* out)
 {
     if (!h || !out) return fail("pkb_state: null argument");
@@ -1558,7 +1120,7 @@ int pkb_state(pkb_env* h, pkb_state_view* out)
     out->pending_bets = h->d.pd;
     out->payoffs = h->d.payoffs;
     out->minimum_raise_value = h->d.mr;
-    out->player_states = h->d.st;
+    out->seat_masks = h->d.sm;
     out->meta = h->d.meta;
     out->hand = h->d.hand;
     out->episode = h->d.episode;

@@ -150,7 +150,7 @@ class Game:
         self.device = self.batch.device
         self._step_count = 0
         # like the reference before reset(): all ACTIVE, zero money (game.py:253-264)
-        self.batch.player_states.fill_(PlayerState.ACTIVE)
+        self.batch.seat_masks.fill_((1 << self.num_players) - 1)  # the ACTIVE field of the seat-mask word
 
     @staticmethod
     def _credits_arg(sc):
