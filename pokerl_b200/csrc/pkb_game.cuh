@@ -469,13 +469,24 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
         }
     } else {
         Dealer d(seed, env_id, episode, v.hand[s]);
-        uint64_t board = 0;
+        uint64_t board = 0, hole[P];
 #pragma unroll
         for (int i = 0; i < 5; ++i) board |= 1ull << d.next();
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const uint64_t hole = (1ull << d.next()) | (1ull << d.next());
-            rk[p] = (todo >> p & 1u) ? eval_mask52_sel_call(board | hole) : PACKED_NONE;
+            hole[p] = (1ull << d.next()) | (1ull << d.next());
+            rk[p] = PACKED_NONE;
+        }
+        // Rank only the seats that show their cards, one per trip: a warp makes as many trips as its busiest lane has
+        // showing seats (typically 2-4), not P of them with most lanes idle.
+        for (uint32_t left = todo; left; left &= left - 1) {
+            const int p = ffs32(left) - 1;
+            uint64_t h = 0;
+#pragma unroll
+            for (int q = 0; q < P; ++q) h = q == p ? hole[q] : h;
+            const uint32_t r = eval_mask52_sel_call(board | h);
+#pragma unroll
+            for (int q = 0; q < P; ++q) rk[q] = q == p ? r : rk[q];
         }
     }
 #pragma unroll

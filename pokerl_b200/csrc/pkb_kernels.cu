@@ -144,17 +144,18 @@ struct Tally {
     uint32_t hands, shows, games, poisoned, invalid, live;
 };
 
-// Step outputs of one finished env: flag bits and the valid mask of the new active player
-// (the valid mask is also cached in the meta word: the next step validates its action against it)
+// Step outputs of one finished env: flag bits and the valid mask of the new active player, into the tile's two output
+// rows (they leave for the caller's arrays with the tile).  The valid mask is also cached in the meta word: the next step
+// validates its action against it.
 template <int P, class V>
-PKB_D uint32_t write_outputs(V& v, int s, const Ctl& c, const StepArgs& a, size_t env, bool skipped = false)
+PKB_D uint32_t write_outputs(V& v, int s, const Ctl& c, uint8_t* out_flags, uint8_t* out_valid, bool skipped = false)
 {
     const uint32_t f = skipped ? F_SKIPPED : (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
-    if (a.flags) a.flags[env] = (uint8_t)f;
+    out_flags[s] = (uint8_t)f;
     const uint32_t w = v.meta[s];
     const uint32_t vm = valid_mask<P>(v, s, unpack_meta(w).act);
     v.meta[s] = (w & ~(127u << 23)) | vm << 23;
-    if (a.valid) a.valid[env] = (uint8_t)vm;
+    out_valid[s] = (uint8_t)vm;
     return f;
 }
 
@@ -249,7 +250,9 @@ struct WarpTile {
     static constexpr size_t OFF_LIST_E = (BUF_BYTES + 15) / 16 * 16;
     static constexpr size_t OFF_LIST_S = OFF_LIST_E + (size_t)T * 4;
     static constexpr size_t OFF_ACT = OFF_LIST_S + (size_t)T;  // u8 per slot: the caller's actions (pkb_step), fetched while the tile loads
-    static constexpr size_t WARP_BYTES = (OFF_ACT + (size_t)T + 127) / 128 * 128;
+    static constexpr size_t OFF_OUT_F = OFF_ACT + (size_t)T;    // u8 per slot: the step's flag byte ...
+    static constexpr size_t OFF_OUT_V = OFF_OUT_F + (size_t)T;  // ... and valid mask, written to the caller's arrays with the tile
+    static constexpr size_t WARP_BYTES = (OFF_OUT_V + (size_t)T + 127) / 128 * 128;
     static constexpr size_t HEADER = 128;
     static constexpr size_t BYTES = HEADER + WARP_BYTES * WARPS;
     static constexpr int THREADS = 32 * WARPS;
@@ -280,6 +283,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     uint32_t* list_e = reinterpret_cast<uint32_t*>(buf + L::OFF_LIST_E);
     uint8_t* list_s = buf + L::OFF_LIST_S;
     uint8_t* act_row = buf + L::OFF_ACT;
+    uint8_t* out_f = buf + L::OFF_OUT_F;
+    uint8_t* out_v = buf + L::OFF_OUT_V;
+    // whole words of the caller's output arrays can be written at once when both arrays are 4-byte aligned
+    const bool out_words = ((reinterpret_cast<uintptr_t>(a.flags) | reinterpret_cast<uintptr_t>(a.valid)) & 3u) == 0;
     View<T> v = tile_view<L>(buf);
     uint32_t* ep = reinterpret_cast<uint32_t*>(buf + L::OFF_EP);
     const uint32_t lanes_below = (1u << lane) - 1u;
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 }
                 if (c.pc == PC_DONE) {
                     tl.poisoned += (uint32_t)c.poisoned;
-                    write_outputs<P>(v, s, c, a, env, skipped);
+                    write_outputs<P>(v, s, c, out_f, out_v, skipped);
                 }
             }
             const bool in_e = live && c.pc != PC_DONE, in_s = live && c.pc == PC_SHOWDOWN;
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                         v.meta[s] = pack_meta(m);
                     }
                     if (!again) {
-                        const uint32_t f = write_outputs<P>(v, s, c, a, env);
+                        const uint32_t f = write_outputs<P>(v, s, c, out_f, out_v);
                         tl.games += (f & F_GAME_OVER) ? 1u : 0u;
                         tl.poisoned += (uint32_t)c.poisoned;
                     }
@@ -485,6 +492,18 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
         fence_async_smem();
         __syncwarp();
+        if (out_words && base + T <= d.n) {  // the two output rows: one 32-bit store per lane and 32 slots
+#pragma unroll
+            for (int w = lane; w < T / 4; w += 32) {
+                if (a.flags) reinterpret_cast<uint32_t*>(a.flags + base)[w] = reinterpret_cast<const uint32_t*>(out_f)[w];
+                if (a.valid) reinterpret_cast<uint32_t*>(a.valid + base)[w] = reinterpret_cast<const uint32_t*>(out_v)[w];
+            }
+        } else {
+            for (int s = lane; s < T && base + s < d.n; s += 32) {
+                if (a.flags) a.flags[base + s] = out_f[s];
+                if (a.valid) a.valid[base + s] = out_v[s];
+            }
+        }
         PKB_WTICK(3);
         if (lane == 0) {
             tma_store_2d(&a.maps.w64, (int)base, 0, buf_s + (uint32_t)L::OFF_CR);
