@@ -407,8 +407,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // that the load after this tile's stores finds it there instead of waiting on HBM with the buffer empty.
         if (lane == 0 && next < a.num_tiles) {
             const int nb = (int)(next * (uint32_t)T);
-            tma_prefetch_2d(&a.maps.w64, nb, 0);
-            tma_prefetch_2d(&a.maps.u32, nb, 0);
+            tma_prefetch_2d(&a.maps.w64, nb, 0);  // the 8-byte rows are 85 % of the tile; the rest rides on the load itself
         }
 #endif
 

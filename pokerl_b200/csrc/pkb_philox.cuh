@@ -147,14 +147,17 @@ PKB_HD int pick_weighted(uint32_t word, uint32_t valid_mask, const uint32_t* wei
     return pick;
 }
 
-// uniform weights: the t-th valid move, t = mulhi32(word, number of valid moves).  The position of
-// the t-th set bit equals the number of inclusive bit prefixes that hold at most t set bits.
+// uniform weights: the t-th valid move, t = mulhi32(word, number of valid moves) -- the position of the t-th set bit of
+// the 7-bit mask, found by halving (low 4 bits, then 2, then 1)
 PKB_HD int pick_uniform(uint32_t word, uint32_t valid_mask)
 {
-    const uint32_t t = mulhi32(word, (uint32_t)popc32(valid_mask));
+    uint32_t t = mulhi32(word, (uint32_t)popc32(valid_mask)), w = valid_mask;
     int pick = 0;
-#pragma unroll
-    for (int a = 0; a < NUM_MOVES - 1; ++a) pick += (uint32_t)popc32(valid_mask & ((2u << a) - 1u)) <= t ? 1 : 0;
+    uint32_t c = (uint32_t)popc32(w & 0xfu);
+    if (t >= c) { t -= c; w >>= 4; pick = 4; }
+    c = (uint32_t)popc32(w & 0x3u);
+    if (t >= c) { t -= c; w >>= 2; pick += 2; }
+    if (t >= (w & 1u)) pick += 1;
     return pick;
 }
 

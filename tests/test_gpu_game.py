@@ -329,3 +329,24 @@ def test_step_u8_equals_step_i32():
             assert np.allclose(sa[k], sb[k], rtol=0, atol=1e-6)
         else:
             assert sa[k] == sb[k], k
+
+
+@pytest.mark.gpu
+def test_seat_masks_decode_to_player_states():
+    """The zero-copy seat-mask words (pkb_state_view.seat_masks: ACTIVE | CALLED<<16 | ALL_IN<<32 | BROKEN<<48) decode to
+    exactly what pkb_player_states returns (the reference's one PlayerState value per seat, enums.py:130-134)."""
+    from pokerl_b200 import GameBatch
+    N, P = 5000, 6
+    g = GameBatch(N, P, [3, 9, 30, 50, 80, 120], 4, 2, seed=8, auto_reset=False)
+    g.reset()
+    for t in range(60):
+        g.step_random(t, [10, 30, 30, 5, 5, 5, 45])
+    m = g.seat_masks.cpu().numpy().astype(np.uint64)
+    st = g.player_states.cpu().numpy()
+    seen = set()
+    for p in range(P):
+        dec = sum(((m >> np.uint64(16 * k + p)) & np.uint64(1)).astype(np.uint8) * v for k, v in enumerate((1, 2, 3, 4)))
+        assert np.array_equal(dec, st[p]), p
+        seen |= set(np.unique(st[p]).tolist())
+    assert seen == {0, 1, 2, 3, 4}  # every PlayerState occurs in this run
+    assert not (m >> np.uint64(16 + P) & np.uint64((1 << (16 - P)) - 1)).any()  # no bits beyond the table's seats
