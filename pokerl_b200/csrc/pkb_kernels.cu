@@ -217,6 +217,11 @@ __device__ unsigned long long g_wrp[4096][12];  // per warp of the last launch: 
 #define PKB_WT_STATIC_ROUNDS 2  // a warp's first tiles are fixed (global warp index + k * warps); the dispenser serves the rest
 #endif
 static_assert(PKB_WT_STATIC_ROUNDS >= 1, "a warp's first tile is always its global index");
+#ifndef PKB_WT_UNROLL_A
+#define PKB_WT_UNROLL_A 1  // pass A stays one rolled loop: the hot code has to fit the instruction cache
+#endif
+#define PKB_PRAGMA_(x) _Pragma(#x)
+#define PKB_UNROLL(n) PKB_PRAGMA_(unroll n)
 #ifndef PKB_WT_WARPS_LARGE
 #define PKB_WT_WARPS_LARGE 2  // P >= 5
 #endif
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         const bool shared_draw = SAMPLE && T <= 128 && ((a.gc.env_id_base + (uint32_t)base) & (uint32_t)(T - 1)) == 0;
         U4 draw{0, 0, 0, 0};
         if (shared_draw) draw = sample_block(a.gc.seed, gid0, a.step_idx);
-#pragma unroll 1
+        PKB_UNROLL(PKB_WT_UNROLL_A)
         for (int s = lane; s < T; s += 32) {
             const size_t env = base + s;
             const bool live = env < d.n;
