@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(num_players=2, start_credits=100, big_blind=2, small_blind=1, seed=0)
 ENVS_PER_GPU = 1 << 20
 RESIDENT_BATCHES = 3  # 3 x 86 MB of env state per GPU: larger than the 126 MB L2
+E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "6"))       # env batches the end-to-end leg keeps in flight (a batch's step waits for its own copies)
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -222,7 +223,7 @@ def run_ours(args, rank, local_rank, world):
     def make_batch(j=0):
         # global env ids: every batch of every rank has its own contiguous slice
         return GameBatch(N, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
-                         seed=WORKLOAD["seed"], env_id_base=(rank * RESIDENT_BATCHES + j) * N, auto_reset=True,
+                         seed=WORKLOAD["seed"], env_id_base=(rank * max(RESIDENT_BATCHES, E2E_BATCHES) + j) * N, auto_reset=True,
                          device=local_rank)
 
     def barrier():
@@ -323,13 +324,15 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- end to end through the public API with HOST buffers.  Every step: H2D copy of that step's actions from
     # pinned host memory, GameBatch.step, D2H copy of its flags and valid masks.  As in the device-resident leg, the
-    # three independent resident batches take turns, each on its own stream, so one batch's copies overlap another
-    # batch's step (a caller that keeps several env batches in flight does exactly this); the actions are a
-    # recording of the device-side random agents, so every one of them is valid for the state it meets.
-    R = max(1, min(K, 126) // RESIDENT_BATCHES)  # rounds; E = R * RESIDENT_BATCHES steps
-    E = R * RESIDENT_BATCHES
+    # independent resident batches take turns, each on its own stream, so one batch's copies overlap another batch's
+    # step (a caller that keeps several env batches in flight does exactly this; within a batch, copy-in -> step ->
+    # copy-out is a serial chain, so E2E_BATCHES of them are in flight); the actions are a recording of the
+    # device-side random agents, so every one of them is valid for the state it meets.
+    R = max(1, min(K, 126) // E2E_BATCHES)  # rounds; E = R * E2E_BATCHES steps
+    E = R * E2E_BATCHES
+    e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(E2E_BATCHES)]
     host_actions, runs = [], []
-    for j in range(RESIDENT_BATCHES):
+    for j in range(E2E_BATCHES):
         rec = make_batch(j)
         rec.reset()
         ha = torch.empty((R, N), dtype=torch.uint8).pin_memory()  # one byte per action (pkb_step_u8)
@@ -342,19 +345,19 @@ def run_ours(args, rank, local_rank, world):
         run = make_batch(j)
         run.reset()
         runs.append(run)
-    dev_actions = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(RESIDENT_BATCHES)]
-    host_out = [torch.empty((2, N), dtype=torch.uint8).pin_memory() for _ in range(RESIDENT_BATCHES)]  # flags, valid
+    dev_actions = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(E2E_BATCHES)]
+    host_out = [torch.empty((2, N), dtype=torch.uint8).pin_memory() for _ in range(E2E_BATCHES)]  # flags, valid
     barrier()
     t0 = time.perf_counter()
-    for st in streams:
+    for st in e2e_streams:
         st.wait_stream(main)
     for r in range(R):
-        for j in range(RESIDENT_BATCHES):
-            with torch.cuda.stream(streams[j]):
+        for j in range(E2E_BATCHES):
+            with torch.cuda.stream(e2e_streams[j]):
                 dev_actions[j].copy_(host_actions[j][r], non_blocking=True)
                 runs[j].step(dev_actions[j])
                 host_out[j].copy_(runs[j].outputs, non_blocking=True)
-    for st in streams:
+    for st in e2e_streams:
         st.synchronize()
     e2e_s = time.perf_counter() - t0
     rejected = sum(run.stats()["invalid"] for run in runs)
@@ -411,7 +414,7 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": N,
                 "d2h_bytes_per_step": 2 * N, "steps": E,
                 "path": "per step: one byte per action H2D from pinned host -> GameBatch.step -> pkb_step_u8 -> flags+valid D2H (one copy) to pinned host; "
-                        "the three resident batches take turns on three streams, host synchronises at the end"},
+                        f"{E2E_BATCHES} resident batches take turns on {E2E_BATCHES} streams, host synchronises at the end"},
         "gpu_launches": K,  # one persistent step_warp_kernel launch per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",
