@@ -58,7 +58,10 @@ struct StepArgs {
     uint32_t num_tiles;
 };
 
-constexpr int STRIDE_ALIGN = 1024;  // env-count granularity of the HBM planes: a multiple of every tile size
+#ifndef PKB_STRIDE_ALIGN
+#define PKB_STRIDE_ALIGN 1024
+#endif
+constexpr int STRIDE_ALIGN = PKB_STRIDE_ALIGN;  // env-count granularity of the HBM planes: a multiple of every tile size
 
 PKB_D View<0> global_view(const DevState& d)
 {
@@ -355,12 +358,17 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 
         // ---- pass A: every slot
         uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
-        // the action draws of a lane's slots come from ONE Philox block when the tile starts on a multiple of 128 (or of
-        // 64 for the 64-env tiles) in global env ids, which it does unless env_id_base is odd-sized (pkb_philox.cuh)
+        // The action draws of a lane's slots: envs whose ids differ only in bits 5-6 share a Philox block (pkb_philox.cuh),
+        // so the slots lane, lane+32, ... of a tile need the block of the 128-aligned id group the tile starts in and,
+        // if the tile runs past that group's end, the next group's: one or two blocks per lane and tile instead of one
+        // per slot (tiles of up to 160 envs span at most two groups).
         const uint32_t gid0 = a.gc.env_id_base + (uint32_t)base + (uint32_t)lane;
-        const bool shared_draw = SAMPLE && T <= 128 && ((a.gc.env_id_base + (uint32_t)base) & (uint32_t)(T - 1)) == 0;
-        U4 draw{0, 0, 0, 0};
-        if (shared_draw) draw = sample_block(a.gc.seed, gid0, a.step_idx);
+        const bool shared_draw = SAMPLE && T <= 160;
+        U4 draw{0, 0, 0, 0}, draw_next{0, 0, 0, 0};
+        if (shared_draw) {
+            draw = sample_block(a.gc.seed, gid0, a.step_idx);
+            if (((gid0 + (uint32_t)(T - 32)) ^ gid0) & ~127u) draw_next = sample_block(a.gc.seed, (gid0 | 127u) + 1u + (gid0 & 31u), a.step_idx);
+        }
         PKB_UNROLL(PKB_WT_UNROLL_A)
         for (int s = lane; s < T; s += 32) {
             const size_t env = base + s;
@@ -374,7 +382,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 int action;
                 if (SAMPLE) {
                     const uint32_t gid = a.gc.env_id_base + (uint32_t)env;
-                    const uint32_t word = shared_draw ? sample_word_of(draw, gid) : sample_word(a.gc.seed, gid, a.step_idx);
+                    const uint32_t word = shared_draw ? sample_word_of(((gid ^ gid0) & ~127u) ? draw_next : draw, gid)
+                                                      : sample_word(a.gc.seed, gid, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     if (a.actions_out) a.actions_out[env] = action;
                 } else {
