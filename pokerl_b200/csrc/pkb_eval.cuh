@@ -43,7 +43,9 @@ PKB_HD uint32_t suit_ranks(uint64_t m, int suit)
     return (x >> 1) | ((x & 1u) << 12);
 }
 
-PKB_HD_CALL uint32_t eval_mask52(uint64_t m)
+// `special` = false leaves out the straight-flush tracker and the two wheel cases (judger.py:83-90): what remains is a
+// function of the rank multiset and, through `fl`, of a flush suit's rank set -- the evaluator tables are built from it.
+PKB_HD uint32_t eval_mask52_impl(uint64_t m, bool special)
 {
     if (m == 0) return PACKED_NONE;  // judger.py:30
     const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
@@ -55,12 +57,14 @@ PKB_HD_CALL uint32_t eval_mask52(uint64_t m)
     const uint32_t run = sx & ~(sx + (sx & (0u - sx)));
 
     const uint32_t st5 = any & (any << 1) & (any << 2) & (any << 3) & (any << 4);  // bit i: ranks i-3..i+1 all present
-    if (run == 0xFu) {                                                              // judger.py:83-85
-        if (sx & 0x1000u) return (HR_STRAIGHT_FLUSH << 20) | 4u;
-    } else if (st5 == 0 && (any & 0x1000u) && (any & ~(any + (any & (0u - any)))) == 0xFu)  // judger.py:86-88
-        return (HR_STRAIGHT << 20) | 4u;
+    if (special) {
+        if (run == 0xFu) {  // judger.py:83-85
+            if (sx & 0x1000u) return (HR_STRAIGHT_FLUSH << 20) | 4u;
+        } else if (st5 == 0 && (any & 0x1000u) && (any & ~(any + (any & (0u - any)))) == 0xFu)  // judger.py:86-88
+            return (HR_STRAIGHT << 20) | 4u;
 
-    if (popc32(run) >= 5) return (HR_STRAIGHT_FLUSH << 20) | (uint32_t)(topbit32(run) + 1);  // judger.py:90
+        if (popc32(run) >= 5) return (HR_STRAIGHT_FLUSH << 20) | (uint32_t)(topbit32(run) + 1);  // judger.py:90
+    }
 
     // rank multiplicities, bit-sliced
     const uint32_t a01 = s0 & s1, x01 = s0 ^ s1, a23 = s2 & s3, x23 = s2 ^ s3;
@@ -94,6 +98,7 @@ PKB_HD_CALL uint32_t eval_mask52(uint64_t m)
     }
     return (HR_HIGH << 20) | pack_top(any, 5, 0);  // :99
 }
+PKB_HD_CALL uint32_t eval_mask52(uint64_t m) { return eval_mask52_impl(m, true); }
 
 // ---- table-driven form of eval_mask52 (the batch kernels: tables staged in shared memory) ------------
 //
@@ -176,6 +181,104 @@ PKB_HD uint32_t eval_mask52_tbl(uint64_t m, const uint32_t* __restrict__ tbl)
     r = wheel ? (HR_STRAIGHT << 20) | 4u : r;
     r = run_is_wheel_low && (sx & 0x1000u) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;
     return m == 0 ? PACKED_NONE : r;
+}
+
+// ---- perfect-hash form for SEVEN-card hands (the batch evaluator kernels) --------------------------------------
+//
+// Away from its three special cases the judger's value is a function of (a) the rank multiset when no suit holds five
+// cards, (b) the flush suit's rank set when one does (seven cards with five of a suit cannot hold four of a kind or a
+// full house).  The special cases (judger.py:83-90) need two more bits: whether the seven ranks contain A-2-3-4-5
+// without a six and without any five-run, and whether the LOWEST maximal run of suit X (the flush suit, else the
+// lowest-numbered suit present) is exactly 5-4-3-2.
+//   (a) 13 rank keys whose sums are distinct over all 49,205 seven-card rank multisets (checked when the table is
+//       built, eval_nf_table_fill) index a table of packed values: key sum <= 7,825,759.  The key sum of a hand is the
+//       sum over its four suits of a per-suit sum, read from two tiny tables (low 7 ranks, high 6 ranks).
+//   (b) an 8192-entry table indexed by the flush suit's rank set: top five ranks | high rank of a >= 5 lowest-run << 20 |
+//       (lowest run == 5-4-3-2) << 24.
+// eval7_hash returns exactly eval_mask52(m) for every mask with seven bits set (hostcheck: all C(52,7)).
+constexpr uint32_t RANK_KEY[13] = {0u, 1u, 5u, 22u, 98u, 453u, 2031u, 8698u, 22854u, 83661u, 262349u, 636345u, 1479181u};
+constexpr uint32_t EVAL_NF_SIZE = 4u * 1479181u + 3u * 636345u + 1u;  // largest key sum + 1 = 7,825,760
+constexpr int EVAL_KLO_SIZE = 128, EVAL_KHI_SIZE = 64;                // key sums of the low 7 / high 6 ranks of a suit
+
+inline uint32_t rank_key_sum(uint32_t x)  // host side (table building); x: 13-bit rank set, bit i = rank i+1
+{
+    uint32_t s = 0;
+    for (int i = 0; i < 13; ++i) s += (x >> i & 1u) ? RANK_KEY[i] : 0u;
+    return s;
+}
+PKB_HD uint32_t low_run(uint32_t x) { return x & ~(x + (x & (0u - x))); }  // the lowest maximal run of consecutive ranks
+
+PKB_HD uint32_t flush_table_entry(uint32_t fl)
+{
+    const uint32_t run = low_run(fl);
+    return pack_top(fl, 5, 0) | (popc32(run) >= 5 ? (uint32_t)(topbit32(run) + 1) : 0u) << 20 | (run == 0xFu ? 1u : 0u) << 24;
+}
+
+// host side: fills nf[EVAL_NF_SIZE] (every seven-card rank multiset -> its value without the special cases) and returns
+// the number of multisets written; 0 if two multisets collide (the keys would be wrong)
+inline uint32_t eval_nf_table_fill(uint32_t* nf)
+{
+    for (uint32_t i = 0; i < EVAL_NF_SIZE; ++i) nf[i] = 0;
+    uint32_t written = 0;
+    int cnt[13] = {0};
+    bool ok = true;
+    // depth-first over the counts of the 13 ranks, 0..4 each, 7 in all
+    struct Rec {
+        static void go(int r, int left, int* cnt, uint32_t* nf, uint32_t& written, bool& ok)
+        {
+            if (r == 13) {
+                if (left) return;
+                // a representative hand without a flush: every card goes to the emptiest suit its rank does not use yet
+                int load[4] = {0, 0, 0, 0};
+                uint64_t m = 0;
+                uint32_t key = 0;
+                for (int q = 0; q < 13; ++q) {
+                    uint32_t used = 0;
+                    for (int j = 0; j < cnt[q]; ++j) {
+                        int best = -1;
+                        for (int su = 0; su < 4; ++su)
+                            if (!(used >> su & 1u) && (best < 0 || load[su] < load[best])) best = su;
+                        used |= 1u << best;
+                        ++load[best];
+                        const int rank0 = q == 12 ? 0 : q + 1;  // rank set bit q = rank q+1; the ace (bit 12) is card rank0 0
+                        m |= 1ull << (13 * best + rank0);
+                        key += RANK_KEY[q];
+                    }
+                }
+                if (load[0] >= 5 || load[1] >= 5 || load[2] >= 5 || load[3] >= 5 || nf[key]) { ok = false; return; }
+                nf[key] = eval_mask52_impl(m, false);
+                ++written;
+                return;
+            }
+            for (int c = 0; c <= 4 && c <= left; ++c) {
+                cnt[r] = c;
+                go(r + 1, left - c, cnt, nf, written, ok);
+            }
+            cnt[r] = 0;
+        }
+    };
+    Rec::go(0, 7, cnt, nf, written, ok);
+    return ok ? written : 0u;
+}
+
+PKB_HD uint32_t eval7_hash(uint64_t m, const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi,
+                           const uint32_t* __restrict__ nf, const uint32_t* __restrict__ flt)
+{
+    const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
+    const uint32_t any = s0 | s1 | s2 | s3;
+    const uint32_t key = klo[s0 & 127u] + khi[s0 >> 7] + klo[s1 & 127u] + khi[s1 >> 7] + klo[s2 & 127u] + khi[s2 >> 7] +
+                         klo[s3 & 127u] + khi[s3 >> 7];
+    const uint32_t fl = popc32(s0) >= 5 ? s0 : popc32(s1) >= 5 ? s1 : popc32(s2) >= 5 ? s2 : popc32(s3) >= 5 ? s3 : 0u;
+    const uint32_t e = flt[fl];
+    const uint32_t sx = s0 ? s0 : s1 ? s1 : s2 ? s2 : s3;  // suit X when there is no flush
+    const bool run_is_wheel_low = fl ? (e >> 24 & 1u) != 0 : low_run(sx) == 0xFu;
+    const bool rank_wheel = (any & (any << 1) & (any << 2) & (any << 3) & (any << 4)) == 0 && (any & 0x1000u) && low_run(any) == 0xFu;
+    uint32_t r = fl ? (HR_FLUSH << 20) | (e & 0xFFFFFu) : nf[key];             // judger.py:91-99
+    const uint32_t sf_hi = e >> 20 & 15u;
+    r = (fl && sf_hi) ? (HR_STRAIGHT_FLUSH << 20) | sf_hi : r;                 // :90
+    r = (rank_wheel && !run_is_wheel_low) ? (HR_STRAIGHT << 20) | 4u : r;      // :86-88
+    r = (run_is_wheel_low && fl && (fl & 0x1000u)) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;  // :83-85 (five of suit X: a flush)
+    return r;
 }
 
 // ---- select form of eval_mask52 (the step kernels) -----------------------------------------------------

@@ -702,6 +702,46 @@ eval_masks_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __re
     }
 }
 
+// ---- the perfect-hash evaluator for seven-card hands (pkb_eval.cuh): tables in global memory, built once per device ----
+struct EvalHashTables {
+    const uint32_t* nf;   // [EVAL_NF_SIZE]  rank-multiset key sum -> packed value (31 MB: stays in the 126 MB L2)
+    const uint32_t* flt;  // [8192]          flush suit's rank set -> top five ranks, straight-flush / wheel-low bits
+    const uint32_t* klo;  // [128]           key sum of the low seven ranks of a suit
+    const uint32_t* khi;  // [64]            key sum of the high six ranks of a suit
+};
+
+PKB_D void stage_key_tables(const EvalHashTables& t, uint32_t* s_klo, uint32_t* s_khi)
+{
+    for (int i = threadIdx.x; i < EVAL_KLO_SIZE; i += blockDim.x) s_klo[i] = t.klo[i];
+    for (int i = threadIdx.x; i < EVAL_KHI_SIZE; i += blockDim.x) s_khi[i] = t.khi[i];
+    __syncthreads();
+}
+
+// seven cards: the hash; anything else (fewer cards, the empty hand): the select evaluator
+PKB_D uint32_t eval_any(uint64_t m, const EvalHashTables& t, const uint32_t* s_klo, const uint32_t* s_khi)
+{
+    return popc64(m) == 7 ? eval7_hash(m, s_klo, s_khi, t.nf, t.flt) : eval_mask52_sel(m);
+}
+
+// eval_hand on id masks: 8 B in, 4 B out per hand; two hands per thread per trip (128-bit loads, 64-bit stores)
+__global__ void __launch_bounds__(EVAL_THREADS)
+eval_masks_hash_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __restrict__ out, EvalHashTables t)
+{
+    __shared__ uint32_t s_klo[EVAL_KLO_SIZE], s_khi[EVAL_KHI_SIZE];
+    stage_key_tables(t, s_klo, s_khi);
+    const uint64_t pairs = n / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(masks) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    if (aligned) {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+            const ulonglong2 m = reinterpret_cast<const ulonglong2*>(masks)[i];
+            reinterpret_cast<uint2*>(out)[i] = make_uint2(eval_any(m.x, t, s_klo, s_khi), eval_any(m.y, t, s_klo, s_khi));
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) out[n - 1] = eval_any(masks[n - 1], t, s_klo, s_khi);
+    } else {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = eval_any(masks[i], t, s_klo, s_khi);
+    }
+}
+
 __constant__ uint64_t c_binom[53][8];  // C(n, k) for n <= 52, k <= 7
 
 // index -> k-subset of {0..51} in colex order (combinatorial number system)
@@ -729,13 +769,15 @@ constexpr int EXH_CHUNK = 32;  // hands per thread; 6-bit category counters stay
 // all C(52,k) hands, enumerated on chip: 0 bytes in, 4 bytes out (optional)
 __global__ void __launch_bounds__(256)
 eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restrict__ out, unsigned long long* hist,
-                       unsigned long long* sums)
+                       unsigned long long* sums, EvalHashTables tabs)
 {
     __shared__ unsigned long long s_hist[11], s_sum[2];
     __shared__ __align__(16) uint32_t s_tbl[EVAL_TABLE_SIZE];
+    __shared__ uint32_t s_klo[EVAL_KLO_SIZE], s_khi[EVAL_KHI_SIZE];
     if (threadIdx.x < 11) s_hist[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_sum[threadIdx.x] = 0;
-    stage_eval_table(s_tbl);
+    if (k == 7) stage_key_tables(tabs, s_klo, s_khi);  // seven cards: the perfect hash; fewer: the rank-set table
+    else stage_eval_table(s_tbl);
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t lo = t * EXH_CHUNK;
     unsigned long long cats = 0, sum_a = 0, sum_b = 0;
@@ -743,7 +785,7 @@ eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restri
         const int todo = (int)(count - lo < EXH_CHUNK ? count - lo : EXH_CHUNK);
         uint64_t m = unrank_colex(first + lo, k);
         for (int j = 0; j < todo; ++j) {
-            const uint32_t p = eval_mask52_tbl(m, s_tbl);
+            const uint32_t p = k == 7 ? eval7_hash(m, s_klo, s_khi, tabs.nf, tabs.flt) : eval_mask52_tbl(m, s_tbl);
             if (out) out[lo + j] = p;
             cats += 1ull << (6 * (p >> 20));
             sum_a += p;
@@ -1252,15 +1294,59 @@ static cudaError_t ensure_eval_table(cudaStream_t s)
     return e;
 }
 
+// builds the perfect-hash evaluator's tables on the current device the first time a batch evaluator runs there
+// (host: 49,205 rank multisets through the product's own evaluator, ~30 ms; then one 31 MB upload)
+static cudaError_t ensure_eval_hash_tables(EvalHashTables* out)
+{
+    static EvalHashTables tabs[64];
+    static bool ready[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!ready[dev]) {
+        const size_t words = (size_t)EVAL_NF_SIZE + 8192 + EVAL_KLO_SIZE + EVAL_KHI_SIZE;
+        uint32_t* host = static_cast<uint32_t*>(malloc(words * 4));
+        if (!host) return cudaErrorMemoryAllocation;
+        if (eval_nf_table_fill(host) != 49205u) {
+            free(host);
+            return cudaErrorUnknown;  // the rank keys collide: cannot happen with the keys in pkb_eval.cuh
+        }
+        uint32_t* h_flt = host + EVAL_NF_SIZE;
+        uint32_t* h_klo = h_flt + 8192;
+        uint32_t* h_khi = h_klo + EVAL_KLO_SIZE;
+        for (uint32_t x = 0; x < 8192u; ++x) h_flt[x] = flush_table_entry(x);
+        for (uint32_t x = 0; x < (uint32_t)EVAL_KLO_SIZE; ++x) h_klo[x] = rank_key_sum(x);
+        for (uint32_t x = 0; x < (uint32_t)EVAL_KHI_SIZE; ++x) h_khi[x] = rank_key_sum(x << 7);
+        uint32_t* dptr = nullptr;
+        e = cudaMalloc(&dptr, words * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(dptr, host, words * 4, cudaMemcpyHostToDevice);
+        free(host);
+        if (e != cudaSuccess) return e;
+        tabs[dev] = EvalHashTables{dptr, dptr + EVAL_NF_SIZE, dptr + EVAL_NF_SIZE + 8192, dptr + EVAL_NF_SIZE + 8192 + EVAL_KLO_SIZE};
+        ready[dev] = true;
+    }
+    *out = tabs[dev];
+    return cudaSuccess;
+}
+
 int pkb_eval_masks(const uint64_t* masks, uint64_t n, uint32_t* out, void* stream)
 {
     if (n == 0) return 0;
     if (!out || !masks) return fail("pkb_eval_masks: null argument");
-    PKB_CUDA(ensure_eval_table(static_cast<cudaStream_t>(stream)));
-    // persistent grid: six 256-thread blocks per SM (the 32 KB table each), grid-stride over the hands
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static const bool use_table = getenv("PKB_EVAL_IMPL") && !strcmp(getenv("PKB_EVAL_IMPL"), "table");
     const uint64_t want = (n / 2 + EVAL_THREADS - 1) / EVAL_THREADS;
-    const unsigned grid = (unsigned)(want < 148ull * 6 ? (want ? want : 1) : 148ull * 6);
-    eval_masks_kernel<<<grid, EVAL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(masks, n, out);
+    if (use_table) {  // the rank-set-table evaluator (comparison): six 256-thread blocks per SM, the 32 KB table each
+        PKB_CUDA(ensure_eval_table(s));
+        const unsigned grid = (unsigned)(want < 148ull * 6 ? (want ? want : 1) : 148ull * 6);
+        eval_masks_kernel<<<grid, EVAL_THREADS, 0, s>>>(masks, n, out);
+    } else {
+        EvalHashTables t;
+        PKB_CUDA(ensure_eval_hash_tables(&t));
+        const unsigned grid = (unsigned)(want < 148ull * 8 ? (want ? want : 1) : 148ull * 8);
+        eval_masks_hash_kernel<<<grid, EVAL_THREADS, 0, s>>>(masks, n, out, t);
+    }
     PKB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1293,12 +1379,14 @@ int pkb_eval_exhaustive(int32_t k, uint64_t first, uint64_t count, uint64_t* his
     PKB_CUDA(ensure_binom());
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PKB_CUDA(ensure_eval_table(s));
+    EvalHashTables t;
+    PKB_CUDA(ensure_eval_hash_tables(&t));
     unsigned long long* d_acc = nullptr;
     PKB_CUDA(cudaMalloc(&d_acc, 13 * 8));
     cudaError_t e = cudaMemsetAsync(d_acc, 0, 13 * 8, s);
     if (e == cudaSuccess && count) {
         const uint64_t threads = (count + EXH_CHUNK - 1) / EXH_CHUNK;
-        eval_exhaustive_kernel<<<blocks_for(threads, 256), 256, 0, s>>>(k, first, count, out, d_acc, d_acc + 11);
+        eval_exhaustive_kernel<<<blocks_for(threads, 256), 256, 0, s>>>(k, first, count, out, d_acc, d_acc + 11, t);
         e = cudaGetLastError();
     }
     unsigned long long host[13];

@@ -47,6 +47,28 @@ uint64_t hc_eval_sel_mismatches(int k, uint64_t first_index_unused, uint64_t cou
     }
     return bad;
 }
+// the perfect-hash seven-card evaluator of the batch kernels, tables built with the product's own functions:
+// mismatches against the bitmask evaluator over the first `count` seven-card hands; -1 if the rank keys collide
+long long hc_eval_hash_mismatches(uint64_t count)
+{
+    static uint32_t* nf = nullptr;
+    static uint32_t klo[pkb::EVAL_KLO_SIZE], khi[pkb::EVAL_KHI_SIZE], flt[8192];
+    if (!nf) {
+        nf = new uint32_t[pkb::EVAL_NF_SIZE];
+        if (pkb::eval_nf_table_fill(nf) != 49205u) return -1;
+        for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KLO_SIZE; ++x) klo[x] = pkb::rank_key_sum(x);
+        for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KHI_SIZE; ++x) khi[x] = pkb::rank_key_sum(x << 7);
+        for (uint32_t x = 0; x < 8192u; ++x) flt[x] = pkb::flush_table_entry(x);
+    }
+    uint64_t m = (1ull << 7) - 1;
+    long long bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        bad += pkb::eval7_hash(m, klo, khi, nf, flt) != pkb::eval_mask52(m);
+        const uint64_t c = m & -m, r = m + c;
+        m = (((r ^ m) >> 2) / c) | r;
+    }
+    return bad;
+}
 uint32_t hc_eval_cards(const uint8_t* c, int n) { return pkb::eval_cards(c, n); }
 uint32_t hc_eval_cards_literal(const uint8_t* c, int n) { return pkb::eval_cards_literal(c, n); }
 
