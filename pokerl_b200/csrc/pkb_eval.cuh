@@ -195,7 +195,10 @@ PKB_HD uint32_t eval_mask52_tbl(uint64_t m, const uint32_t* __restrict__ tbl)
 //       sum over its four suits of a per-suit sum, read from two tiny tables (low 7 ranks, high 6 ranks).
 //   (b) an 8192-entry table indexed by the flush suit's rank set: top five ranks | high rank of a >= 5 lowest-run << 20 |
 //       (lowest run == 5-4-3-2) << 24.
-// eval7_hash returns exactly eval_mask52(m) for every mask with seven bits set (hostcheck: all C(52,7)).
+// eval7_hash3 (below) returns exactly eval_mask52(m) for every mask with seven bits set (hostcheck: all C(52,7)).
+// The seven-card rank wheel needs no table: two more cards cannot complete another five-run, so it is "A,2,3,4,5 present,
+// six absent".  (Measured and not kept: one 8192-entry key table per raw suit slice in shared memory instead of the two
+// tiny ones -- fewer instructions, but 32 KB per block leaves no L1 for the value table: 112 G evals/s against 163.)
 constexpr uint32_t RANK_KEY[13] = {0u, 1u, 5u, 22u, 98u, 453u, 2031u, 8698u, 22854u, 83661u, 262349u, 636345u, 1479181u};
 constexpr uint32_t EVAL_NF_SIZE = 4u * 1479181u + 3u * 636345u + 1u;  // largest key sum + 1 = 7,825,760
 constexpr int EVAL_KLO_SIZE = 128, EVAL_KHI_SIZE = 64;                // key sums of the low 7 / high 6 ranks of a suit
@@ -261,23 +264,87 @@ inline uint32_t eval_nf_table_fill(uint32_t* nf)
     return ok ? written : 0u;
 }
 
-PKB_HD uint32_t eval7_hash(uint64_t m, const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi,
-                           const uint32_t* __restrict__ nf, const uint32_t* __restrict__ flt)
+// Dense form of the value table.  Only 49,205 of the 7.8 M key sums occur, one per 32-byte sector: a 1.5 MB working set
+// that misses the L1.  A displacement hash packs them into 65,536 slots (256 KB):
+//     slot(key) = (key * (0x9E3779B1 + 2 * disp[key >> EVAL_DISP_SHIFT])) >> 16          (32-bit product)
+// i.e. one odd multiplier per bucket of 256 consecutive key sums, found greedily (largest bucket first) when the tables
+// are built: eval_dense_table_fill.  Both tables stay cache resident (61 KB + 256 KB).
+constexpr int EVAL_DISP_SHIFT = 8;
+constexpr uint32_t EVAL_DISP_SIZE = (EVAL_NF_SIZE >> EVAL_DISP_SHIFT) + 1;  // 15,286 buckets
+constexpr uint32_t EVAL_DENSE_SIZE = 65536;
+PKB_HD uint32_t dense_slot(uint32_t key, uint32_t disp) { return (key * (0x9E3779B1u + 2u * disp)) >> 16; }
+
+// host side: nf[EVAL_NF_SIZE] (from eval_nf_table_fill; 0 = key sum does not occur) -> disp[EVAL_DISP_SIZE], dense[EVAL_DENSE_SIZE];
+// false if some bucket found no displacement (does not happen with these constants)
+inline bool eval_dense_table_fill(const uint32_t* nf, uint16_t* disp, uint32_t* dense)
+{
+    struct Bucket { uint32_t id, count; };
+    Bucket* order = new Bucket[EVAL_DISP_SIZE];
+    for (uint32_t b = 0; b < EVAL_DISP_SIZE; ++b) order[b] = Bucket{b, 0};
+    for (uint32_t k = 0; k < EVAL_NF_SIZE; ++k) order[k >> EVAL_DISP_SHIFT].count += nf[k] ? 1u : 0u;
+    // counting sort by size, largest first (sizes are small)
+    uint32_t maxc = 0;
+    for (uint32_t b = 0; b < EVAL_DISP_SIZE; ++b) maxc = order[b].count > maxc ? order[b].count : maxc;
+    Bucket* sorted = new Bucket[EVAL_DISP_SIZE];
+    uint32_t n = 0;
+    for (uint32_t c = maxc + 1; c-- > 0;)
+        for (uint32_t b = 0; b < EVAL_DISP_SIZE; ++b)
+            if (order[b].count == c) sorted[n++] = order[b];
+    bool* used = new bool[EVAL_DENSE_SIZE];
+    for (uint32_t i = 0; i < EVAL_DENSE_SIZE; ++i) { used[i] = false; dense[i] = 0; }
+    for (uint32_t b = 0; b < EVAL_DISP_SIZE; ++b) disp[b] = 0;
+    bool ok = true;
+    for (uint32_t i = 0; i < EVAL_DISP_SIZE && ok; ++i) {
+        const Bucket bk = sorted[i];
+        if (!bk.count) break;
+        const uint32_t lo = bk.id << EVAL_DISP_SHIFT, hi = (lo + (1u << EVAL_DISP_SHIFT)) < EVAL_NF_SIZE ? lo + (1u << EVAL_DISP_SHIFT) : EVAL_NF_SIZE;
+        uint32_t d = 0;
+        for (; d < 65536u; ++d) {
+            bool fits = true;
+            for (uint32_t k = lo; k < hi && fits; ++k)
+                if (nf[k]) {
+                    const uint32_t sl = dense_slot(k, d);
+                    if (used[sl]) fits = false;
+                    else  // two keys of the same bucket on one slot?
+                        for (uint32_t k2 = lo; k2 < k; ++k2)
+                            if (nf[k2] && dense_slot(k2, d) == sl) fits = false;
+                }
+            if (fits) break;
+        }
+        if (d == 65536u) { ok = false; break; }
+        disp[bk.id] = (uint16_t)d;
+        for (uint32_t k = lo; k < hi; ++k)
+            if (nf[k]) {
+                const uint32_t sl = dense_slot(k, d);
+                used[sl] = true;
+                dense[sl] = nf[k];
+            }
+    }
+    delete[] order;
+    delete[] sorted;
+    delete[] used;
+    return ok;
+}
+
+// the evaluator proper
+PKB_HD uint32_t eval7_hash3(uint64_t m, const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi,
+                            const uint16_t* __restrict__ disp, const uint32_t* __restrict__ dense, const uint32_t* __restrict__ flt)
 {
     const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
     const uint32_t any = s0 | s1 | s2 | s3;
     const uint32_t key = klo[s0 & 127u] + khi[s0 >> 7] + klo[s1 & 127u] + khi[s1 >> 7] + klo[s2 & 127u] + khi[s2 >> 7] +
                          klo[s3 & 127u] + khi[s3 >> 7];
+    const uint32_t nfv = dense[dense_slot(key, disp[key >> EVAL_DISP_SHIFT])];
     const uint32_t fl = popc32(s0) >= 5 ? s0 : popc32(s1) >= 5 ? s1 : popc32(s2) >= 5 ? s2 : popc32(s3) >= 5 ? s3 : 0u;
     const uint32_t e = flt[fl];
     const uint32_t sx = s0 ? s0 : s1 ? s1 : s2 ? s2 : s3;  // suit X when there is no flush
     const bool run_is_wheel_low = fl ? (e >> 24 & 1u) != 0 : low_run(sx) == 0xFu;
-    const bool rank_wheel = (any & (any << 1) & (any << 2) & (any << 3) & (any << 4)) == 0 && (any & 0x1000u) && low_run(any) == 0xFu;
-    uint32_t r = fl ? (HR_FLUSH << 20) | (e & 0xFFFFFu) : nf[key];             // judger.py:91-99
+    const bool rank_wheel = (any & 0x101Fu) == 0x100Fu;  // A,2,3,4,5 and no six (rank order: bit 12 = ace, bits 0-3 = 2..5, bit 4 = six)
+    uint32_t r = fl ? (HR_FLUSH << 20) | (e & 0xFFFFFu) : nfv;                 // judger.py:91-99
     const uint32_t sf_hi = e >> 20 & 15u;
     r = (fl && sf_hi) ? (HR_STRAIGHT_FLUSH << 20) | sf_hi : r;                 // :90
     r = (rank_wheel && !run_is_wheel_low) ? (HR_STRAIGHT << 20) | 4u : r;      // :86-88
-    r = (run_is_wheel_low && fl && (fl & 0x1000u)) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;  // :83-85 (five of suit X: a flush)
+    r = (run_is_wheel_low && fl && (fl & 0x1000u)) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;  // :83-85
     return r;
 }
 

@@ -702,12 +702,13 @@ eval_masks_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __re
     }
 }
 
-// ---- the perfect-hash evaluator for seven-card hands (pkb_eval.cuh): tables in global memory, built once per device ----
+// ---- the perfect-hash evaluator for seven-card hands (pkb_eval.cuh eval7_hash3): tables built once per device ----
 struct EvalHashTables {
-    const uint32_t* nf;   // [EVAL_NF_SIZE]  rank-multiset key sum -> packed value (31 MB: stays in the 126 MB L2)
-    const uint32_t* flt;  // [8192]          flush suit's rank set -> top five ranks, straight-flush / wheel-low bits
-    const uint32_t* klo;  // [128]           key sum of the low seven ranks of a suit
-    const uint32_t* khi;  // [64]            key sum of the high six ranks of a suit
+    const uint32_t* dense;  // [65536]  slot -> packed value of a rank multiset (256 KB, cache resident)
+    const uint32_t* flt;    // [8192]   flush suit's rank set -> top five ranks, straight-flush / wheel-low bits
+    const uint32_t* klo;    // [128]    key sum of the low seven ranks of a suit (staged in shared memory)
+    const uint32_t* khi;    // [64]     key sum of the high six ranks of a suit (staged in shared memory)
+    const uint16_t* disp;   // [30571]  per 256 key sums: the multiplier offset of the displacement hash (61 KB)
 };
 
 PKB_D void stage_key_tables(const EvalHashTables& t, uint32_t* s_klo, uint32_t* s_khi)
@@ -720,7 +721,7 @@ PKB_D void stage_key_tables(const EvalHashTables& t, uint32_t* s_klo, uint32_t* 
 // seven cards: the hash; anything else (fewer cards, the empty hand): the select evaluator
 PKB_D uint32_t eval_any(uint64_t m, const EvalHashTables& t, const uint32_t* s_klo, const uint32_t* s_khi)
 {
-    return popc64(m) == 7 ? eval7_hash(m, s_klo, s_khi, t.nf, t.flt) : eval_mask52_sel(m);
+    return popc64(m) == 7 ? eval7_hash3(m, s_klo, s_khi, t.disp, t.dense, t.flt) : eval_mask52_sel(m);
 }
 
 // eval_hand on id masks: 8 B in, 4 B out per hand; two hands per thread per trip (128-bit loads, 64-bit stores)
@@ -772,8 +773,9 @@ eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restri
                        unsigned long long* sums, EvalHashTables tabs)
 {
     __shared__ unsigned long long s_hist[11], s_sum[2];
-    __shared__ __align__(16) uint32_t s_tbl[EVAL_TABLE_SIZE];
-    __shared__ uint32_t s_klo[EVAL_KLO_SIZE], s_khi[EVAL_KHI_SIZE];
+    __shared__ __align__(16) uint32_t s_tbl[EVAL_TABLE_SIZE];  // k < 7: the rank-set table; k == 7: its first words hold the key tables
+    uint32_t* s_klo = s_tbl;
+    uint32_t* s_khi = s_tbl + EVAL_KLO_SIZE;
     if (threadIdx.x < 11) s_hist[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_sum[threadIdx.x] = 0;
     if (k == 7) stage_key_tables(tabs, s_klo, s_khi);  // seven cards: the perfect hash; fewer: the rank-set table
@@ -785,7 +787,7 @@ eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restri
         const int todo = (int)(count - lo < EXH_CHUNK ? count - lo : EXH_CHUNK);
         uint64_t m = unrank_colex(first + lo, k);
         for (int j = 0; j < todo; ++j) {
-            const uint32_t p = k == 7 ? eval7_hash(m, s_klo, s_khi, tabs.nf, tabs.flt) : eval_mask52_tbl(m, s_tbl);
+            const uint32_t p = k == 7 ? eval7_hash3(m, s_klo, s_khi, tabs.disp, tabs.dense, tabs.flt) : eval_mask52_tbl(m, s_tbl);
             if (out) out[lo + j] = p;
             cats += 1ull << (6 * (p >> 20));
             sum_a += p;
@@ -1305,16 +1307,25 @@ static cudaError_t ensure_eval_hash_tables(EvalHashTables* out)
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!ready[dev]) {
-        const size_t words = (size_t)EVAL_NF_SIZE + 8192 + EVAL_KLO_SIZE + EVAL_KHI_SIZE;
+        // host: key sum -> value for the 49,205 rank multisets, packed into the dense table by the displacement hash
+        uint32_t* nf = static_cast<uint32_t*>(malloc((size_t)EVAL_NF_SIZE * 4));
+        const size_t words = (size_t)EVAL_DENSE_SIZE + 8192 + EVAL_KLO_SIZE + EVAL_KHI_SIZE + (EVAL_DISP_SIZE + 1) / 2;  // dense | flt | klo | khi | disp (u16)
         uint32_t* host = static_cast<uint32_t*>(malloc(words * 4));
-        if (!host) return cudaErrorMemoryAllocation;
-        if (eval_nf_table_fill(host) != 49205u) {
+        if (!nf || !host) {
+            free(nf);
             free(host);
-            return cudaErrorUnknown;  // the rank keys collide: cannot happen with the keys in pkb_eval.cuh
+            return cudaErrorMemoryAllocation;
         }
-        uint32_t* h_flt = host + EVAL_NF_SIZE;
+        uint32_t* h_flt = host + EVAL_DENSE_SIZE;
         uint32_t* h_klo = h_flt + 8192;
         uint32_t* h_khi = h_klo + EVAL_KLO_SIZE;
+        uint16_t* h_disp = reinterpret_cast<uint16_t*>(h_khi + EVAL_KHI_SIZE);
+        const bool built = eval_nf_table_fill(nf) == 49205u && eval_dense_table_fill(nf, h_disp, host);
+        free(nf);
+        if (!built) {
+            free(host);
+            return cudaErrorUnknown;  // the rank keys collide or a bucket found no multiplier: cannot happen with the constants in pkb_eval.cuh
+        }
         for (uint32_t x = 0; x < 8192u; ++x) h_flt[x] = flush_table_entry(x);
         for (uint32_t x = 0; x < (uint32_t)EVAL_KLO_SIZE; ++x) h_klo[x] = rank_key_sum(x);
         for (uint32_t x = 0; x < (uint32_t)EVAL_KHI_SIZE; ++x) h_khi[x] = rank_key_sum(x << 7);
@@ -1323,7 +1334,9 @@ static cudaError_t ensure_eval_hash_tables(EvalHashTables* out)
         if (e == cudaSuccess) e = cudaMemcpy(dptr, host, words * 4, cudaMemcpyHostToDevice);
         free(host);
         if (e != cudaSuccess) return e;
-        tabs[dev] = EvalHashTables{dptr, dptr + EVAL_NF_SIZE, dptr + EVAL_NF_SIZE + 8192, dptr + EVAL_NF_SIZE + 8192 + EVAL_KLO_SIZE};
+        uint32_t* d_flt = dptr + EVAL_DENSE_SIZE;
+        tabs[dev] = EvalHashTables{dptr, d_flt, d_flt + 8192, d_flt + 8192 + EVAL_KLO_SIZE,
+                                   reinterpret_cast<const uint16_t*>(d_flt + 8192 + EVAL_KLO_SIZE + EVAL_KHI_SIZE)};
         ready[dev] = true;
     }
     *out = tabs[dev];

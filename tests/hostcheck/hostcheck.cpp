@@ -47,15 +47,19 @@ uint64_t hc_eval_sel_mismatches(int k, uint64_t first_index_unused, uint64_t cou
     }
     return bad;
 }
-// the perfect-hash seven-card evaluator of the batch kernels, tables built with the product's own functions:
-// mismatches against the bitmask evaluator over the first `count` seven-card hands; -1 if the rank keys collide
-long long hc_eval_hash_mismatches(uint64_t count)
+// the perfect-hash seven-card evaluator of the batch kernels, tables built with the product's own host code: -1 if the keys collide, -2 if the displacement hash cannot be built
+long long hc_eval_hash3_mismatches(uint64_t count)
 {
     static uint32_t* nf = nullptr;
     static uint32_t klo[pkb::EVAL_KLO_SIZE], khi[pkb::EVAL_KHI_SIZE], flt[8192];
+    static uint16_t* disp = nullptr;
+    static uint32_t* dense = nullptr;
     if (!nf) {
         nf = new uint32_t[pkb::EVAL_NF_SIZE];
         if (pkb::eval_nf_table_fill(nf) != 49205u) return -1;
+        disp = new uint16_t[pkb::EVAL_DISP_SIZE];
+        dense = new uint32_t[pkb::EVAL_DENSE_SIZE];
+        if (!pkb::eval_dense_table_fill(nf, disp, dense)) return -2;
         for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KLO_SIZE; ++x) klo[x] = pkb::rank_key_sum(x);
         for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KHI_SIZE; ++x) khi[x] = pkb::rank_key_sum(x << 7);
         for (uint32_t x = 0; x < 8192u; ++x) flt[x] = pkb::flush_table_entry(x);
@@ -63,7 +67,7 @@ long long hc_eval_hash_mismatches(uint64_t count)
     uint64_t m = (1ull << 7) - 1;
     long long bad = 0;
     for (uint64_t i = 0; i < count; ++i) {
-        bad += pkb::eval7_hash(m, klo, khi, nf, flt) != pkb::eval_mask52(m);
+        bad += pkb::eval7_hash3(m, klo, khi, disp, dense, flt) != pkb::eval_mask52(m);
         const uint64_t c = m & -m, r = m + c;
         m = (((r ^ m) >> 2) / c) | r;
     }

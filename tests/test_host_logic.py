@@ -67,6 +67,16 @@ def test_select_evaluator_equals_bitmask_evaluator(hc, k):
     assert hc.hc_eval_mask_sel(0) == 10 << 20
 
 
+def test_perfect_hash_evaluator_equals_bitmask_evaluator(hc):
+    """The seven-card perfect-hash evaluator of the batch kernels (pkb_eval.cuh eval7_hash3: rank keys with distinct
+    multiset sums, displacement-hashed dense value table, flush table, the judger's special cases as selects), tables
+    built by the product's own host code: equal to the bitmask evaluator on ALL C(52,7) hands.  A negative result means
+    the tables could not be built (colliding keys / no multiplier for a bucket)."""
+    hc.hc_eval_hash3_mismatches.restype = C.c_longlong
+    hc.hc_eval_hash3_mismatches.argtypes = [C.c_uint64]
+    assert hc.hc_eval_hash3_mismatches(133_784_560) == 0
+
+
 def test_all_at_once_deal_equals_sequential_dealer(hc):
     """deal_ids (interleaved Philox blocks + sorted draw chain, P <= 4) deals exactly the cards of the sequential Dealer."""
     rng = np.random.default_rng(3)
