@@ -326,25 +326,33 @@ inline bool eval_dense_table_fill(const uint32_t* nf, uint16_t* disp, uint32_t* 
     return ok;
 }
 
-// the evaluator proper
+// the evaluator proper.  All tables are indexed by RAW 13-bit suit slices of the id mask (bit 0 = ace, bit 1 = two, ..), so
+// no slice is rotated into rank order on the way: klo/khi by the low seven / high six bits of a slice, flt by the whole.
+PKB_HD uint32_t rot_ranks(uint32_t x) { return (x >> 1) | ((x & 1u) << 12); }  // raw suit slice -> rank order (bit i = rank i+1)
+inline uint32_t raw_key_sum(uint32_t x) { return rank_key_sum(rot_ranks(x)); }   // host side (table building)
+
 PKB_HD uint32_t eval7_hash3(uint64_t m, const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi,
                             const uint16_t* __restrict__ disp, const uint32_t* __restrict__ dense, const uint32_t* __restrict__ flt)
 {
-    const uint32_t s0 = suit_ranks(m, 0), s1 = suit_ranks(m, 1), s2 = suit_ranks(m, 2), s3 = suit_ranks(m, 3);
-    const uint32_t any = s0 | s1 | s2 | s3;
-    const uint32_t key = klo[s0 & 127u] + khi[s0 >> 7] + klo[s1 & 127u] + khi[s1 >> 7] + klo[s2 & 127u] + khi[s2 >> 7] +
-                         klo[s3 & 127u] + khi[s3 >> 7];
+    const uint32_t x0 = (uint32_t)m & 0x1fffu, x1 = (uint32_t)(m >> 13) & 0x1fffu, x2 = (uint32_t)(m >> 26) & 0x1fffu,
+                   x3 = (uint32_t)(m >> 39) & 0x1fffu;
+    const uint32_t key = klo[x0 & 127u] + khi[x0 >> 7] + klo[x1 & 127u] + khi[x1 >> 7] + klo[x2 & 127u] + khi[x2 >> 7] +
+                         klo[x3 & 127u] + khi[x3 >> 7];
     const uint32_t nfv = dense[dense_slot(key, disp[key >> EVAL_DISP_SHIFT])];
-    const uint32_t fl = popc32(s0) >= 5 ? s0 : popc32(s1) >= 5 ? s1 : popc32(s2) >= 5 ? s2 : popc32(s3) >= 5 ? s3 : 0u;
+    const uint32_t fl = popc32(x0) >= 5 ? x0 : popc32(x1) >= 5 ? x1 : popc32(x2) >= 5 ? x2 : popc32(x3) >= 5 ? x3 : 0u;
     const uint32_t e = flt[fl];
-    const uint32_t sx = s0 ? s0 : s1 ? s1 : s2 ? s2 : s3;  // suit X when there is no flush
-    const bool run_is_wheel_low = fl ? (e >> 24 & 1u) != 0 : low_run(sx) == 0xFu;
-    const bool rank_wheel = (any & 0x101Fu) == 0x100Fu;  // A,2,3,4,5 and no six (rank order: bit 12 = ace, bits 0-3 = 2..5, bit 4 = six)
+    // A,2,3,4,5 present and no six; with seven cards no other five-run can exist (judger.py:86-88)
+    const bool rank_wheel = ((x0 | x1 | x2 | x3) & 0x3Fu) == 0x1Fu;
+    bool run_is_wheel_low = (e >> 24 & 1u) != 0;  // of the flush suit (entry 0, no flush: false)
+    if (rank_wheel && !fl) {  // rare: the lowest run of suit X = the lowest-numbered suit present
+        const uint32_t sx = x0 ? x0 : x1 ? x1 : x2 ? x2 : x3;
+        run_is_wheel_low = low_run(rot_ranks(sx)) == 0xFu;
+    }
     uint32_t r = fl ? (HR_FLUSH << 20) | (e & 0xFFFFFu) : nfv;                 // judger.py:91-99
     const uint32_t sf_hi = e >> 20 & 15u;
     r = (fl && sf_hi) ? (HR_STRAIGHT_FLUSH << 20) | sf_hi : r;                 // :90
     r = (rank_wheel && !run_is_wheel_low) ? (HR_STRAIGHT << 20) | 4u : r;      // :86-88
-    r = (run_is_wheel_low && fl && (fl & 0x1000u)) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;  // :83-85
+    r = (run_is_wheel_low && fl && (fl & 1u)) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;  // :83-85 (raw bit 0 = the ace)
     return r;
 }
 

@@ -1326,9 +1326,9 @@ static cudaError_t ensure_eval_hash_tables(EvalHashTables* out)
             free(host);
             return cudaErrorUnknown;  // the rank keys collide or a bucket found no multiplier: cannot happen with the constants in pkb_eval.cuh
         }
-        for (uint32_t x = 0; x < 8192u; ++x) h_flt[x] = flush_table_entry(x);
-        for (uint32_t x = 0; x < (uint32_t)EVAL_KLO_SIZE; ++x) h_klo[x] = rank_key_sum(x);
-        for (uint32_t x = 0; x < (uint32_t)EVAL_KHI_SIZE; ++x) h_khi[x] = rank_key_sum(x << 7);
+        for (uint32_t x = 0; x < 8192u; ++x) h_flt[x] = flush_table_entry(rot_ranks(x));  // all three indexed by RAW suit slices
+        for (uint32_t x = 0; x < (uint32_t)EVAL_KLO_SIZE; ++x) h_klo[x] = raw_key_sum(x);
+        for (uint32_t x = 0; x < (uint32_t)EVAL_KHI_SIZE; ++x) h_khi[x] = raw_key_sum(x << 7);
         uint32_t* dptr = nullptr;
         e = cudaMalloc(&dptr, words * 4);
         if (e == cudaSuccess) e = cudaMemcpy(dptr, host, words * 4, cudaMemcpyHostToDevice);

@@ -60,9 +60,9 @@ long long hc_eval_hash3_mismatches(uint64_t count)
         disp = new uint16_t[pkb::EVAL_DISP_SIZE];
         dense = new uint32_t[pkb::EVAL_DENSE_SIZE];
         if (!pkb::eval_dense_table_fill(nf, disp, dense)) return -2;
-        for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KLO_SIZE; ++x) klo[x] = pkb::rank_key_sum(x);
-        for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KHI_SIZE; ++x) khi[x] = pkb::rank_key_sum(x << 7);
-        for (uint32_t x = 0; x < 8192u; ++x) flt[x] = pkb::flush_table_entry(x);
+        for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KLO_SIZE; ++x) klo[x] = pkb::raw_key_sum(x);
+        for (uint32_t x = 0; x < (uint32_t)pkb::EVAL_KHI_SIZE; ++x) khi[x] = pkb::raw_key_sum(x << 7);
+        for (uint32_t x = 0; x < 8192u; ++x) flt[x] = pkb::flush_table_entry(pkb::rot_ranks(x));
     }
     uint64_t m = (1ull << 7) - 1;
     long long bad = 0;
