@@ -725,7 +725,13 @@ PKB_D uint32_t eval_any(uint64_t m, const EvalHashTables& t, const uint32_t* s_k
 }
 
 // eval_hand on id masks: 8 B in, 4 B out per hand; two hands per thread per trip (128-bit loads, 64-bit stores)
-__global__ void __launch_bounds__(EVAL_THREADS)
+#ifndef PKB_EVAL_MIN_BLOCKS
+#define PKB_EVAL_MIN_BLOCKS 8  // full residency (32 registers): the kernel waits on its three gathers per hand
+#endif
+#ifndef PKB_EVAL_UNROLL
+#define PKB_EVAL_UNROLL 1
+#endif
+__global__ void __launch_bounds__(EVAL_THREADS, PKB_EVAL_MIN_BLOCKS)
 eval_masks_hash_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __restrict__ out, EvalHashTables t)
 {
     __shared__ uint32_t s_klo[EVAL_KLO_SIZE], s_khi[EVAL_KHI_SIZE];
@@ -733,6 +739,7 @@ eval_masks_hash_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t*
     const uint64_t pairs = n / 2, stride = (uint64_t)gridDim.x * blockDim.x;
     const bool aligned = (reinterpret_cast<uintptr_t>(masks) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
     if (aligned) {
+        PKB_UNROLL(PKB_EVAL_UNROLL)
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
             const ulonglong2 m = reinterpret_cast<const ulonglong2*>(masks)[i];
             reinterpret_cast<uint2*>(out)[i] = make_uint2(eval_any(m.x, t, s_klo, s_khi), eval_any(m.y, t, s_klo, s_khi));
@@ -1357,7 +1364,7 @@ int pkb_eval_masks(const uint64_t* masks, uint64_t n, uint32_t* out, void* strea
     } else {
         EvalHashTables t;
         PKB_CUDA(ensure_eval_hash_tables(&t));
-        const unsigned grid = (unsigned)(want < 148ull * 8 ? (want ? want : 1) : 148ull * 8);
+        const unsigned grid = (unsigned)(want < 148ull * PKB_EVAL_MIN_BLOCKS ? (want ? want : 1) : 148ull * PKB_EVAL_MIN_BLOCKS);
         eval_masks_hash_kernel<<<grid, EVAL_THREADS, 0, s>>>(masks, n, out, t);
     }
     PKB_CUDA(cudaGetLastError());
