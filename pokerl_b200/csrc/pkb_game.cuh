@@ -489,9 +489,10 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
             for (int q = 0; q < P; ++q) rk[q] = q == p ? r : rk[q];
         }
     }
+    double bet0[P];  // self.bets: the order of the layers (:496) goes by the bets as they were
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        b[p] = v.bt[p * ld + s];  // :485 working copy
+        b[p] = bet0[p] = v.bt[p * ld + s];  // :485 working copy
         pay[p] = 0.0;
     }
     int n = c.npw;
@@ -501,7 +502,7 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
         bool have = false;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            const double bi = v.bt[i * ld + s];
+            const double bi = bet0[i];
             if ((todo >> i & 1u) && (!have || bi < least)) { p = i; least = bi; have = true; }
         }
         todo &= ~(1u << p);
