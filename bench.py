@@ -12,8 +12,8 @@ sample+step kernel (pkb::step_warp_kernel).  Envs shard by contiguous global-id 
 (weak scaling); one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
 
 Timing: W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket, timed with
-one CUDA event pair; the reported time is the max over ranks.  One 2^20-env batch (86 MB of state)
-would fit the 126 MB L2, so each GPU holds THREE such batches (258 MB, "inputs larger than L2") and
+one CUDA event pair; the reported time is the max over ranks.  One 2^20-env batch (96 MB of state)
+would fit the 126 MB L2, so each GPU holds THREE such batches (289 MB, "inputs larger than L2") and
 steps them round-robin: every step is one pass of the hot path over one batch of 2^20 envs whose
 state was pushed out of L2 by the steps of the other two batches, i.e. it streams from HBM and back.
 The batches are independent, so each one is stepped on its own CUDA stream: the drain of one step's
@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(num_players=2, start_credits=100, big_blind=2, small_blind=1, seed=0)
 ENVS_PER_GPU = 1 << 20
-RESIDENT_BATCHES = 3  # 3 x 86 MB of env state per GPU: larger than the 126 MB L2
+RESIDENT_BATCHES = 3  # 3 x 96 MB of env state per GPU: larger than the 126 MB L2
 E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "6"))       # env batches the end-to-end leg keeps in flight (a batch's step waits for its own copies)
 L2_FLUSH_BYTES = 256 << 20
 
@@ -196,7 +196,7 @@ def workload_config(envs_per_gpu, world, note=None):
            "auto_reset": True, "seed": WORKLOAD["seed"], "sharding": f"env-sliced x{world}, no data-path collective",
            "resident_batches_per_gpu": RESIDENT_BATCHES,
            "l2": f"inputs larger than L2: {RESIDENT_BATCHES} batches of {envs_per_gpu} envs per GPU "
-                 f"({RESIDENT_BATCHES * 86 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2) stepped round-robin, "
+                 f"({RESIDENT_BATCHES * 96 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2) stepped round-robin, "
                  "one batch per step"}
     if note:
         cfg["note"] = note
@@ -418,7 +418,7 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": K,  # one persistent step_warp_kernel launch per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",
-                        "note": "one batch stepped back to back: its 86 MB of state stays in the 126 MB L2"},
+                        "note": "one batch stepped back to back: its 96 MB of state stays in the 126 MB L2"},
         "flushed_by_memset": {"value": N * world / (flushed_ms / 1e3), "unit": "env-steps/s", "us_per_step": flushed_ms * 1e3,
                               "note": "one batch, 256 MB memset before every step, each step timed on its own: the step "
                                       "also pays for writing the memset's dirty lines out of L2"},
