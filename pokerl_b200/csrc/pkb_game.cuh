@@ -213,10 +213,23 @@ PKB_HD void setup_hand(V& v, size_t s, Seats& x, Meta& m, const GameConst& gc)
     m.turn = 0;
     x.active = all_seats<P>() & ~x.broken;  // :421
     x.called = x.allin = 0;
-    m.dealer = first_playing<P>(x, m.dealer + 1);  // :432
-    m.sb = first_playing<P>(x, m.dealer + 1);      // :433
-    m.bb = first_playing<P>(x, m.sb + 1);          // :434
-    m.act = first_playing<P>(x, m.bb + 1);         // :435
+    if constexpr (P == 2) {
+        // :432-435 for two seats.  first_playing(idx) is seat idx (mod 2) when both seats or neither are alive, else the
+        // one alive seat whatever idx: so dealer, small blind, big blind and first actor alternate d^1, d, d^1, d, or all
+        // four are the alive seat.
+        const uint32_t alive = 3u & ~x.broken;
+        const bool by_index = alive == 3u || alive == 0u;
+        const int only = alive == 1u ? 0 : 1, d = m.dealer & 1;
+        m.dealer = by_index ? d ^ 1 : only;
+        m.sb = by_index ? d : only;
+        m.bb = by_index ? d ^ 1 : only;
+        m.act = by_index ? d : only;
+    } else {
+        m.dealer = first_playing<P>(x, m.dealer + 1);  // :432
+        m.sb = first_playing<P>(x, m.dealer + 1);      // :433
+        m.bb = first_playing<P>(x, m.sb + 1);          // :434
+        m.act = first_playing<P>(x, m.bb + 1);         // :435
+    }
     set_state(x, m.bb, ST_CALLED);                 // :441
     double hb = 0.0;
 #pragma unroll
