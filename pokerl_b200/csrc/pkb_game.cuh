@@ -350,7 +350,7 @@ PKB_D uint32_t cyclic_interval(int act, int cur)
 // One Game.next_turn (game.py:541-576) up to the point where it would call end_hand (turn == 4);
 // returns false when the step must stop here (loop cap, or end_hand is due).
 template <int P, class V>
-PKB_D bool next_turn_once(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
+PKB_D bool next_turn_once(V& v, size_t s, Seats& x, Meta& m, Ctl& c, bool committed = false)
 {
     m.act = c.cur;
     if (c.nt >= NEXT_TURN_CAP) {  // the reference has no termination guarantee here
@@ -358,7 +358,7 @@ PKB_D bool next_turn_once(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
         return false;
     }
     ++c.nt;
-    commit<P>(v, s);  // :554-558
+    if (!committed) commit<P>(v, s);  // :554-558 (step_begin has done it already for the step's first next_turn)
     m.turn += 1;      // :561
     if (m.turn == 4) {  // :563-565 -> end_hand, then `return game_over, True, True`
         c.pc = PC_END_HAND;
@@ -383,29 +383,39 @@ PKB_D bool next_turn_once(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
 // merges), and the search restarts from the same seat.  So if the search fails again, every further
 // next_turn fails the same way until turn == 4 ("streets skipped"): the
 // remaining streets are run out in closed form.
+// the part of seat_scan after its search has found no ACTIVE seat (c.pc == PC_DONE on entry); `committed`: the caller
+// has already done the commit of the first next_turn
+template <int P, class V>
+PKB_D void seat_scan_miss(V& v, size_t s, Seats& x, Meta& m, Ctl& c, bool committed)
+{
+    if (!next_turn_once<P>(v, s, x, m, c, committed)) return;
+    uint32_t cand = x.active & cyclic_interval<P>(m.act, c.cur);
+    if (!cand) {
+        const int more = 4 - m.turn;  // next_turn calls until turn == 4
+        if (c.nt + more <= NEXT_TURN_CAP) {
+            c.nt += more;
+            m.turn = 4;
+            m.act = c.cur;
+            c.pc = PC_END_HAND;
+            c.cont = 1;
+            return;
+        }
+        do {  // the loop cap falls inside the run-out: step through it call by call
+            if (!next_turn_once<P>(v, s, x, m, c)) return;
+            cand = x.active & cyclic_interval<P>(m.act, c.cur);
+        } while (!cand);
+    }
+    m.act = first_from_p<P>(cand, m.act);
+}
+
 template <int P, class V>
 PKB_D void seat_scan(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
 {
     c.pc = PC_DONE;
-    uint32_t cand = x.active & cyclic_interval<P>(m.act, c.cur);
+    const uint32_t cand = x.active & cyclic_interval<P>(m.act, c.cur);
     if (!cand) {
-        if (!next_turn_once<P>(v, s, x, m, c)) return;
-        cand = x.active & cyclic_interval<P>(m.act, c.cur);
-        if (!cand) {
-            const int more = 4 - m.turn;  // next_turn calls until turn == 4
-            if (c.nt + more <= NEXT_TURN_CAP) {
-                c.nt += more;
-                m.turn = 4;
-                m.act = c.cur;
-                c.pc = PC_END_HAND;
-                c.cont = 1;
-                return;
-            }
-            do {  // the loop cap falls inside the run-out: step through it call by call
-                if (!next_turn_once<P>(v, s, x, m, c)) return;
-                cand = x.active & cyclic_interval<P>(m.act, c.cur);
-            } while (!cand);
-        }
+        seat_scan_miss<P>(v, s, x, m, c, false);
+        return;
     }
     m.act = first_from_p<P>(cand, m.act);
 }
@@ -422,14 +432,23 @@ PKB_D void step_begin(V& v, size_t s, Seats& x, Meta& m, Ctl& c, int action, uin
         return;
     }
     apply_action<P>(v, s, x, m.act, action, hb, credit, gc);
-    if (popc32(x.active | x.called | x.allin) > 1) {  // :598-605
+    const bool contested = popc32(x.active | x.called | x.allin) > 1;  // :598
+    uint32_t cand = 0;
+    if (contested) {  // :599-605
         c.cur = m.act;
         m.act = m.act + 1 == P ? 0 : m.act + 1;
-        seat_scan<P>(v, s, x, m, c);
-    } else {  // :616-619
+        cand = x.active & cyclic_interval<P>(m.act, c.cur);
+    }
+    // Both ways on from here start with the same commit -- next_turn (nobody left to act, :554-558) and end_hand after
+    // a fold (:457-461) -- so it is done once, for whichever lanes need it, instead of at two places with few lanes each.
+    if (!cand) commit<P>(v, s);
+    if (!contested) {  // :616-619; end_hand_begin(.., committed = true)
         c.pc = PC_END_HAND;
         c.cont = 0;
-    }
+    } else if (cand)
+        m.act = first_from_p<P>(cand, m.act);
+    else
+        seat_scan_miss<P>(v, s, x, m, c, true);
 }
 
 // Game.end_hand, first part (game.py:453-482): commit, count the potential winners, settle a
@@ -437,12 +456,12 @@ PKB_D void step_begin(V& v, size_t s, Seats& x, Meta& m, Ctl& c, int action, uin
 // From here until setup_hand the PENDING plane carries self.payoffs (it is all zero after commit and
 // is rewritten by the next setup_hand), so no per-seat register array crosses a phase boundary.
 template <int P, class V>
-PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c)
+PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c, bool committed = false)
 {
     const size_t ld = v.ld();
     // :457-461; pending (= payoffs from here on) is 0.0 afterwards, :468.  When end_hand is entered from
     // next_turn (c.cont) that call has just committed: pending and the minimum raise are already zero.
-    if (!c.cont) commit<P>(v, s);
+    if (!c.cont && !committed) commit<P>(v, s);
     const uint32_t contenders = x.active | x.called | x.allin;  // :471 not BROKEN, not FOLDED
     const int n = popc32(contenders);
     c.npw = n;

@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 tl.invalid += skipped ? 0u : (uint32_t)c.invalid;
                 if (c.pc == PC_END_HAND) {  // end_hand's head (game.py:453-482): it is short, and it decides the list
                     ++tl.hands;
-                    if (end_hand_begin<P>(v, s, x, c)) c.pc = PC_SHOWDOWN;
+                    if (end_hand_begin<P>(v, s, x, c, true)) c.pc = PC_SHOWDOWN;  // step_begin has committed
                 }
                 if (!c.invalid) {  // an invalid action changes nothing (game.py:649-651)
                     store_seats<P>(v, s, x);
