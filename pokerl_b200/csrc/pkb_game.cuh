@@ -571,7 +571,11 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
         } else {  // :516 (S * onehot) / sum(onehot)
             const double k = (double)nw;
 #pragma unroll
-            for (int i = 0; i < P; ++i) pay[i] += __dmul_rn(S, (ws.winners >> i & 1u) ? 1.0 : 0.0) / k;
+            for (int i = 0; i < P; ++i) {
+                const double share = __dmul_rn(S, (ws.winners >> i & 1u) ? 1.0 : 0.0);
+                // two seats can only tie two ways: x / 2.0 == x * 0.5 exactly (no division sequence in the heads-up kernel)
+                pay[i] += P == 2 ? __dmul_rn(share, 0.5) : share / k;
+            }
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) {
