@@ -422,12 +422,14 @@ PKB_D void seat_scan(V& v, size_t s, Seats& x, Meta& m, Ctl& c)
 
 // Game.step up to the first end_hand (game.py:648-699 and 597-605).  `vmask`, `hb`, `credit`: the
 // actor's valid mask and the high bet / stack it was computed from.
-template <int P, class V>
+// CHECKED = false: the action was drawn from `vmask` on the device (pick_uniform / pick_weighted return a valid move by
+// construction), so the validation is left out.
+template <int P, bool CHECKED = true, class V>
 PKB_D void step_begin(V& v, size_t s, Seats& x, Meta& m, Ctl& c, int action, uint32_t vmask, double hb, double credit,
                       const GameConst& gc)
 {
     c = Ctl{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
-    if (action < 0 || action >= NUM_MOVES || !(vmask >> action & 1u)) {  // :648-651, before any mutation
+    if (CHECKED && (action < 0 || action >= NUM_MOVES || !(vmask >> action & 1u))) {  // :648-651, before any mutation
         c.invalid = 1;
         return;
     }

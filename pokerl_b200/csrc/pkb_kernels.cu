@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     action = act_row[s];
                     action = action == 255 ? ACTION_SKIP : action;
                 }
-                step_begin<P>(v, s, x, m, c, action, vm, hb, credit, a.gc);
+                step_begin<P, !SAMPLE>(v, s, x, m, c, action, vm, hb, credit, a.gc);
                 const bool skipped = !SAMPLE && action == ACTION_SKIP;  // rejected like any out-of-range action, but not an error
                 tl.live += skipped ? 0u : 1u;
                 tl.invalid += skipped ? 0u : (uint32_t)c.invalid;
