@@ -362,12 +362,21 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // so the slots lane, lane+32, ... of a tile need the block of the 128-aligned id group the tile starts in and,
         // if the tile runs past that group's end, the next group's: one or two blocks per lane and tile instead of one
         // per slot (tiles of up to 160 envs span at most two groups).
-        const uint32_t gid0 = a.gc.env_id_base + (uint32_t)base + (uint32_t)lane;
-        const bool shared_draw = SAMPLE && T <= 160;
-        U4 draw{0, 0, 0, 0}, draw_next{0, 0, 0, 0};
-        if (shared_draw) {
-            draw = sample_block(a.gc.seed, gid0, a.step_idx);
+        // The words are laid out in slot order here (queue[k] = the draw of slot lane + 32k); pass A takes the head of the
+        // queue and shifts it, so its rolled loop selects nothing.
+        constexpr bool SHARED_DRAW = SAMPLE && T <= 160;
+        constexpr int NQ = SHARED_DRAW ? T / 32 : 1;
+        uint32_t queue[NQ] = {0};
+        if constexpr (SHARED_DRAW) {
+            const uint32_t gid0 = a.gc.env_id_base + (uint32_t)base + (uint32_t)lane;
+            const U4 draw = sample_block(a.gc.seed, gid0, a.step_idx);
+            U4 draw_next{0, 0, 0, 0};
             if (((gid0 + (uint32_t)(T - 32)) ^ gid0) & ~127u) draw_next = sample_block(a.gc.seed, (gid0 | 127u) + 1u + (gid0 & 31u), a.step_idx);
+            const uint32_t w8[8] = {draw.x, draw.y, draw.z, draw.w, draw_next.x, draw_next.y, draw_next.z, draw_next.w};
+            const uint32_t first = gid0 >> 5 & 3u;  // word of the lane's first slot inside its group's block
+#pragma unroll
+            for (int k = 0; k < NQ; ++k)  // slot k takes word first + k of the two blocks (compile-time indices only: registers)
+                queue[k] = first == 0 ? w8[k & 7] : first == 1 ? w8[(k + 1) & 7] : first == 2 ? w8[(k + 2) & 7] : w8[(k + 3) & 7];
         }
         PKB_UNROLL(PKB_WT_UNROLL_A)
         for (int s = lane; s < T; s += 32) {
@@ -381,9 +390,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 const uint32_t vm = m.vm;  // = valid_mask_from(hb, credit, v.mr[s]), left in the meta word by the previous step / reset
                 int action;
                 if (SAMPLE) {
-                    const uint32_t gid = a.gc.env_id_base + (uint32_t)env;
-                    const uint32_t word = shared_draw ? sample_word_of(((gid ^ gid0) & ~127u) ? draw_next : draw, gid)
-                                                      : sample_word(a.gc.seed, gid, a.step_idx);
+                    const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     if (a.actions_out) a.actions_out[env] = action;
                 } else {
@@ -407,6 +414,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     write_outputs<P>(v, s, c, out_f, out_v, skipped);
                 }
             }
+#pragma unroll
+            for (int k = 0; k + 1 < NQ; ++k) queue[k] = queue[k + 1];  // next slot's draw to the head
             const bool in_e = live && c.pc != PC_DONE, in_s = live && c.pc == PC_SHOWDOWN;
             const uint32_t vote_e = __ballot_sync(FULL, in_e), vote_s = __ballot_sync(FULL, in_s);
             if (in_e) list_e[n_e + (uint32_t)__popc(vote_e & lanes_below)] = (uint32_t)s | pack_ctl(c) << 8;
