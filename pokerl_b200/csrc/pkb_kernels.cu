@@ -379,9 +379,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 queue[k] = first == 0 ? w8[k & 7] : first == 1 ? w8[(k + 1) & 7] : first == 2 ? w8[(k + 2) & 7] : w8[(k + 3) & 7];
         }
         PKB_UNROLL(PKB_WT_UNROLL_A)
+        const uint32_t n_live = d.n - base < (size_t)T ? (uint32_t)(d.n - base) : (uint32_t)T;  // slots of this tile that are envs
         for (int s = lane; s < T; s += 32) {
             const size_t env = base + s;
-            const bool live = env < d.n;
+            const bool live = (uint32_t)s < n_live;
             Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
             if (live) {
                 Seats x = load_seats<P>(v, s);
