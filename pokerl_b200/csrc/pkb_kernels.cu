@@ -31,7 +31,10 @@ struct DevState {
     uint32_t *meta, *hand, *episode;
     unsigned long long* stats;  // [STAT_COUNT] counters
     double* payoff_sum;         // [MAX_PLAYERS]
-    uint32_t* sched;            // [2] step kernel: next tile to hand out, blocks that have finished
+    // Cross-launch pipelining of the step kernel (programmatic dependent launch): a step launch may start while
+    // the previous one is still draining, so a tile is guarded by its own epoch word instead of by kernel order.
+    unsigned long long* seq;    // [1] blocks of step launches started so far: block ticket / grid size = the launch's index
+    uint32_t* epoch;            // [tiles] number of step launches that have stored this tile (release/acquire)
     uint64_t n, stride;
 };
 
@@ -124,6 +127,35 @@ PKB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memor
 PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 PKB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 PKB_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PKB_D void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// programmatic dependent launch: lets the next kernel of the stream start once every block of this one has got here
+PKB_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+PKB_D uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+PKB_D void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// Tile hand-over between two step launches that are in flight at the same time.  The launch with index L may load a
+// tile once L launches have stored it; it then publishes L + 1.  The producer is a block of an EARLIER launch of the
+// same stream, and every block of an earlier launch is resident before a later launch starts (that is the launch
+// condition of griddepcontrol), so the wait cannot deadlock; the poll cap turns a broken chain (a failed launch,
+// two streams racing on one handle) into a launch error instead of a hang.
+PKB_D void epoch_wait(const uint32_t* word, uint32_t want)
+{
+    for (uint32_t polls = 0; ld_acquire_u32(word) != want; ++polls) {
+        __nanosleep(64);
+        if (polls > (1u << 22)) __trap();
+    }
+    fence_async_global();  // the tile was written through the async proxy and is about to be read through it
+}
+PKB_D void epoch_publish(uint32_t* word, uint32_t value)
+{
+    bulk_wait_all();       // this thread's TMA stores have been performed ...
+    fence_async_global();  // ... and are ordered before the generic-proxy release below
+    st_release_u32(word, value);
+}
 
 template <class L>
 PKB_D View<L::T> tile_view(unsigned char* smem)
@@ -216,10 +248,6 @@ __device__ unsigned long long g_wrp[4096][12];  // per warp of the last launch: 
 #ifndef PKB_WT_WARPS
 #define PKB_WT_WARPS 4    // warps per block (they only share the block's statistics reduction), P <= 4
 #endif
-#ifndef PKB_WT_STATIC_ROUNDS
-#define PKB_WT_STATIC_ROUNDS 2  // a warp's first tiles are fixed (global warp index + k * warps); the dispenser serves the rest
-#endif
-static_assert(PKB_WT_STATIC_ROUNDS >= 1, "a warp's first tile is always its global index");
 #ifndef PKB_WT_UNROLL_A
 #define PKB_WT_UNROLL_A 1  // pass A stays one rolled loop: the hot code has to fit the instruction cache
 #endif
@@ -299,8 +327,15 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     uint32_t* ep = reinterpret_cast<uint32_t*>(buf + L::OFF_EP);
     const uint32_t lanes_below = (1u << lane) - 1u;
 
+    // Which launch of this handle is this?  Blocks of one launch all start before any block of the next one does
+    // (stream order; with programmatic dependent launch: because launch_dependents comes after the ticket), and every
+    // launch of a handle has the same grid, so the block's ticket divided by the grid size is the launch index.
+    __shared__ uint32_t s_launch;
+    if (threadIdx.x == 0) s_launch = (uint32_t)(atomicAdd(d.seq, 1ull) / gridDim.x);
     if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
+    __syncthreads();
+    const uint32_t launch = s_launch;
+    pdl_launch_dependents();  // the next step launch may start filling the SMs this one's finished blocks leave
 
     Tally<P> tl;
 #pragma unroll
@@ -322,21 +357,20 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 #else
 #define PKB_WTICK(i)
 #endif
-    // the first tile of a warp is its global index; further tiles come from a global dispenser, drawn one tile ahead
+    // A warp's tiles are its global index plus multiples of the warp count: the same tile meets the same warp in every
+    // launch, and launch L + 1 reaches a tile in the order launch L finished them.
     const uint32_t warps_total = gridDim.x * L::WARPS;
     uint32_t tile = blockIdx.x * L::WARPS + warp;
+    uint32_t stored = 0xffffffffu;  // lane 0: the tile whose store is in flight and whose epoch is still to be published
     for (uint32_t it = 0; tile < a.num_tiles; ++it) {
         const size_t base = (size_t)tile * T;
-        if (lane == 0) {  // two TMA box copies bring the tile in
+        if (lane == 0) {  // two TMA box copies bring the tile in, once the previous launch has stored it
+            epoch_wait(&d.epoch[tile], launch);
             mbar_arrive_expect_tx(bar, (uint32_t)L::BUF_BYTES);
             tma_load_2d(buf_s + (uint32_t)L::OFF_CR, &a.maps.w64, (int)base, 0, bar);
             tma_load_2d(buf_s + (uint32_t)L::OFF_META, &a.maps.u32, (int)base, 0, bar);
         }
-        // the tile after this one: fixed for the first rounds (no atomic: thousands of warps asking one counter at the same
-        // moment wait microseconds for the answer), from the dispenser afterwards; lane 0 holds it, consumed after the stores
-        uint32_t next = tile + warps_total;
-        if (it + 1 >= (uint32_t)PKB_WT_STATIC_ROUNDS && lane == 0)
-            next = (uint32_t)PKB_WT_STATIC_ROUNDS * warps_total + atomicAdd(&d.sched[0], 1u);
+        const uint32_t next = tile + warps_total;
         if (!SAMPLE) {  // the caller's actions, as bytes (254: out of range, 255: skip), fetched while the tile is in flight
 #pragma unroll
             for (int k = 0; k < T / 32; ++k) {
@@ -354,6 +388,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             __syncwarp();
         }
         mbar_wait(bar, it & 1u);
+        if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);  // its store finished long ago
         PKB_WTICK(0);
 
         // ---- pass A: every slot
@@ -378,8 +413,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             for (int k = 0; k < NQ; ++k)  // slot k takes word first + k of the two blocks (compile-time indices only: registers)
                 queue[k] = first == 0 ? w8[k & 7] : first == 1 ? w8[(k + 1) & 7] : first == 2 ? w8[(k + 2) & 7] : w8[(k + 3) & 7];
         }
-        PKB_UNROLL(PKB_WT_UNROLL_A)
         const uint32_t n_live = d.n - base < (size_t)T ? (uint32_t)(d.n - base) : (uint32_t)T;  // slots of this tile that are envs
+        PKB_UNROLL(PKB_WT_UNROLL_A)
         for (int s = lane; s < T; s += 32) {
             const size_t env = base + s;
             const bool live = (uint32_t)s < n_live;
@@ -533,15 +568,16 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             tma_store_2d(&a.maps.u32, (int)base, 0, buf_s + (uint32_t)L::OFF_META);
             bulk_commit();
             bulk_wait_read();  // the buffer is about to be refilled
+            stored = tile;
         }
         __syncwarp();
-        tile = __shfl_sync(FULL, next, 0);
+        tile = next;
         PKB_WTICK(4);
 #ifdef PKB_TIMING
         wt_acc[5] += 1;
 #endif
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
 #ifdef PKB_TIMING
     {
         const uint32_t gw = blockIdx.x * L::WARPS + warp;
@@ -560,11 +596,6 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         }
     }
 #endif
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(&d.sched[1], 1u) == gridDim.x - 1) {  // the last block to finish re-arms the dispenser
-        d.sched[0] = 0;
-        d.sched[1] = 0;
-    }
     if (a.gc.track_stats) reduce_stats<P>(d, tl);
 }
 
@@ -877,6 +908,12 @@ struct pkb_env {
     size_t arena_bytes;
     uint32_t* d_weights;
     int sm_count;
+    // The stream of the handle's last launch.  Step launches of one handle hand tiles over through epoch words and derive
+    // their launch index from the order in which their blocks start, so they must start in submission order: a call on a
+    // DIFFERENT stream is first ordered after everything submitted to the previous one.
+    cudaStream_t last_stream;
+    bool has_last;
+    cudaEvent_t order_event;
 };
 
 static thread_local std::string g_error;
@@ -911,6 +948,23 @@ static int fail(const char* what, cudaError_t e = cudaSuccess)
         default: return fail("num_players must be in 2..10");           \
     }
 
+// orders the handle's next launch (on stream s) after its previous ones when the caller has switched streams
+static cudaError_t order_on_stream(pkb_env* h, cudaStream_t s)
+{
+    cudaError_t e = cudaSuccess;
+    if (h->has_last && h->last_stream != s) {
+        e = cudaEventRecord(h->order_event, h->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, h->order_event, 0);
+        if (e != cudaSuccess) {  // the old stream is gone: everything on the device finishes first
+            (void)cudaGetLastError();
+            e = cudaDeviceSynchronize();
+        }
+    }
+    h->last_stream = s;
+    h->has_last = true;
+    return e;
+}
+
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // One launch per step: a persistent grid of as many blocks as fit the device at once.
@@ -933,22 +987,52 @@ static cudaError_t resident_blocks(K kernel, int threads, size_t smem, int devic
     return cudaSuccess;
 }
 
+// Every step launch of a handle -- caller's actions or device sampler -- uses the same grid (the launch index is derived
+// from it on the device), so the resident-block count is the smaller of the two kernel variants'.
+template <int P>
+static cudaError_t step_grid(int device, int sm_count, uint64_t n, unsigned* grid, uint32_t* num_tiles)
+{
+    using L = WarpTile<P>;
+    static int per_sm_t[64] = {0}, per_sm_f[64] = {0};
+    cudaError_t e = resident_blocks(step_warp_kernel<P, true>, L::THREADS, L::BYTES, device, per_sm_t);
+    if (e == cudaSuccess) e = resident_blocks(step_warp_kernel<P, false>, L::THREADS, L::BYTES, device, per_sm_f);
+    if (e != cudaSuccess) return e;
+    int per_sm = per_sm_t[device] < per_sm_f[device] ? per_sm_t[device] : per_sm_f[device];
+    per_sm = per_sm < L::MIN_BLOCKS ? per_sm : L::MIN_BLOCKS;
+    static const bool verbose = getenv("PKB_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "pkb: step kernel P=%d warp tile=%d smem=%zu blocks/SM=%d (compiled for %d)\n", P, L::T, (size_t)L::BYTES, per_sm,
+                L::MIN_BLOCKS);
+    *num_tiles = (uint32_t)((n + L::T - 1) / L::T);
+    const unsigned resident = (unsigned)(per_sm * sm_count);
+    const unsigned want = (*num_tiles + L::WARPS - 1) / L::WARPS;
+    *grid = want < resident ? want : resident;
+    return cudaSuccess;
+}
+
+// One launch per step: a persistent grid of as many blocks as fit the device at once, launched with programmatic stream
+// serialization so that it may start while the previous step launch of the stream is still draining (tiles are handed
+// over one by one through their epoch words, see epoch_wait).
 template <int P, bool SAMPLE>
 static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_count)
 {
     using L = WarpTile<P>;
-    static int blocks_per_sm[64] = {0};
-    cudaError_t e = resident_blocks(step_warp_kernel<P, SAMPLE>, L::THREADS, L::BYTES, device, blocks_per_sm);
+    unsigned grid = 0;
+    cudaError_t e = step_grid<P>(device, sm_count, a.d.n, &grid, &a.num_tiles);
     if (e != cudaSuccess) return e;
-    if (getenv("PKB_VERBOSE"))
-        fprintf(stderr, "pkb: step kernel P=%d warp tile=%d smem=%zu blocks/SM=%d (compiled for %d)\n", P, L::T, (size_t)L::BYTES,
-                blocks_per_sm[device], L::MIN_BLOCKS);
-    a.num_tiles = (uint32_t)((a.d.n + L::T - 1) / L::T);
-    const int per_sm = blocks_per_sm[device] < L::MIN_BLOCKS ? blocks_per_sm[device] : L::MIN_BLOCKS;
-    const unsigned resident = (unsigned)(per_sm * sm_count);
-    const unsigned want = (a.num_tiles + L::WARPS - 1) / L::WARPS;
-    step_warp_kernel<P, SAMPLE><<<want < resident ? want : resident, L::THREADS, L::BYTES, s>>>(a);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(L::THREADS);
+    cfg.dynamicSmemBytes = L::BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("PKB_NO_PDL") != nullptr;  // measurement switch: plain stream order between step launches
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, step_warp_kernel<P, SAMPLE>, a);
 }
 
 // ---- TMA descriptors (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----
@@ -1027,7 +1111,9 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     // arena: 8-byte planes (f64 money, seat masks) | u32 planes | stats
     const size_t n_w64 = (size_t)(4 * P + 2) * stride, n_u32 = (size_t)3 * stride;
     const size_t off_u32 = n_w64 * 8, off_stats = (off_u32 + n_u32 * 4 + 255) / 256 * 256;
-    h->arena_bytes = off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 2 * 4;
+    const size_t off_seq = (off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 255) / 256 * 256;
+    const size_t n_epoch = stride / 32;  // one word per tile; tiles hold at least 32 envs
+    h->arena_bytes = off_seq + 256 + n_epoch * 4;
     cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
     if (e != cudaSuccess) {
         delete h;
@@ -1055,7 +1141,8 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     d.stats = reinterpret_cast<unsigned long long*>(base + off_stats);
     d.payoff_sum = reinterpret_cast<double*>(base + off_stats + STAT_COUNT * 8);
     h->d_weights = reinterpret_cast<uint32_t*>(base + off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8);
-    d.sched = h->d_weights + NUM_MOVES + 1;
+    d.seq = reinterpret_cast<unsigned long long*>(base + off_seq);
+    d.epoch = reinterpret_cast<uint32_t*>(base + off_seq + 256);
     d.n = n;
     d.stride = stride;
 
@@ -1082,6 +1169,14 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
         delete h;
         return fail("pkb_create: cuTensorMapEncodeTiled failed");
     }
+    h->has_last = false;
+    h->last_stream = nullptr;
+    e = cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaFree(h->arena);
+        delete h;
+        return fail("pkb_create: cudaEventCreate", e);
+    }
     *out = h;
     return 0;
 }
@@ -1090,7 +1185,8 @@ int pkb_destroy(pkb_env* h)
 {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->arena);
+    cudaFree(h->arena);  // waits for the handle's launches
+    cudaEventDestroy(h->order_event);
     delete h;
     return 0;
 }
@@ -1110,6 +1206,7 @@ int pkb_reset(pkb_env* h, const uint8_t* env_mask, void* stream)
     if (!h) return fail("pkb_reset: null handle");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     PKB_DISPATCH_P(h->cfg.num_players, (reset_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, h->gc, env_mask)));
     PKB_CUDA(cudaGetLastError());
     return 0;
@@ -1134,6 +1231,7 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.use_weights = weights ? 1u : 0u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     cudaError_t e = cudaSuccess;
     PKB_DISPATCH_P(h->cfg.num_players,
                    e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count)
@@ -1163,6 +1261,7 @@ int pkb_sample_actions(pkb_env* h, uint32_t step_idx, const uint32_t* weights, i
     if (!h || !actions_out) return fail("pkb_sample_actions: null argument");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     if (weights) PKB_CUDA(cudaMemcpyAsync(h->d_weights, weights, NUM_MOVES * 4, cudaMemcpyHostToDevice, s));
     PKB_DISPATCH_P(h->cfg.num_players, (sample_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(
                                            h->d, h->gc, step_idx, weights ? 1u : 0u, h->d_weights, actions_out)));
@@ -1176,6 +1275,7 @@ int pkb_valid_actions(pkb_env* h, int32_t player, uint8_t* valid, void* stream)
     if (player >= h->cfg.num_players) return fail("pkb_valid_actions: player out of range");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     PKB_DISPATCH_P(h->cfg.num_players, (valid_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, player, valid)));
     PKB_CUDA(cudaGetLastError());
     return 0;
@@ -1186,6 +1286,7 @@ int pkb_game_over(pkb_env* h, uint8_t* out, void* stream)
     if (!h || !out) return fail("pkb_game_over: null argument");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     PKB_DISPATCH_P(h->cfg.num_players, (game_over_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, out)));
     PKB_CUDA(cudaGetLastError());
     return 0;
@@ -1196,6 +1297,7 @@ int pkb_player_states(pkb_env* h, uint8_t* out, void* stream)
     if (!h || !out) return fail("pkb_player_states: null argument");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     PKB_DISPATCH_P(h->cfg.num_players, (player_states_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, out)));
     PKB_CUDA(cudaGetLastError());
     return 0;
@@ -1225,6 +1327,7 @@ int pkb_cards(pkb_env* h, uint8_t* out, void* stream)
     if (!h || !out) return fail("pkb_cards: null argument");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     PKB_DISPATCH_P(h->cfg.num_players, (cards_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, h->gc, out)));
     PKB_CUDA(cudaGetLastError());
     return 0;
@@ -1236,6 +1339,7 @@ int pkb_hand_features(pkb_env* h, int32_t player, uint32_t* out, void* stream)
     if (player >= h->cfg.num_players) return fail("pkb_hand_features: player out of range");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     PKB_DISPATCH_P(h->cfg.num_players,
                    (features_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d, h->gc, player, out)));
     PKB_CUDA(cudaGetLastError());
@@ -1247,6 +1351,7 @@ int pkb_stats(pkb_env* h, pkb_stats_t* out, void* stream)
     if (!h || !out) return fail("pkb_stats: null argument");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
     unsigned long long c[STAT_COUNT];
     double ps[MAX_PLAYERS];
     PKB_CUDA(cudaMemcpyAsync(c, h->d.stats, sizeof c, cudaMemcpyDeviceToHost, s));
@@ -1266,6 +1371,7 @@ int pkb_stats_reset(pkb_env* h, void* stream)
 {
     if (!h) return fail("pkb_stats_reset: null handle");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
+    PKB_CUDA(order_on_stream(h, static_cast<cudaStream_t>(stream)));
     PKB_CUDA(cudaMemsetAsync(h->d.stats, 0, STAT_COUNT * 8 + MAX_PLAYERS * 8, static_cast<cudaStream_t>(stream)));
     return 0;
 }
