@@ -481,55 +481,63 @@ PKB_D bool end_hand_begin(V& v, size_t s, const Seats& x, Ctl& c, bool committed
     return true;
 }
 
-// Game.end_hand, ranked showdown (game.py:483-528).
-// The working copy of bets is kept in registers; payoffs are written to the pending plane at the end.
+// Game.end_hand, ranked showdown (game.py:483-528), in three phases so that each one runs with every lane busy on its own
+// kind of work item:
+//   showdown_deal    one lane per hand: replays the deal and parks the board / hole-card masks in the hand's own tile rows
+//   showdown_rank    one lane per (hand, seat): eval_hand(board + hole) of one seat (judger.py:7-99)
+//   showdown_settle  one lane per hand: the side-pot loop (game.py:496-528)
+// Scratch: after end_hand's commit the PENDING row of every seat and the minimum raise are 0.0 and stay unread until
+// showdown_settle writes the payoffs into PENDING (minimum raise is rewritten by setup_hand), so the 8-byte words
+// pd[p] hold seat p's hole-card mask, then its packed rank, and mr holds the board mask.
 template <int P, class V>
-PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed, uint32_t env_id, uint32_t episode)
+PKB_D void showdown_deal(V& v, size_t s, uint64_t seed, uint32_t env_id, uint32_t episode)
+{
+    const size_t ld = v.ld();
+    uint64_t* pd = reinterpret_cast<uint64_t*>(v.pd);
+    uint64_t board = 0;
+    if constexpr (5 + 2 * P <= 13) {  // small tables: interleaved Philox blocks, sorted draw chain
+        uint32_t id[5 + 2 * P];
+        deal_ids<5 + 2 * P>(seed, env_id, episode, v.hand[s], id);
+        board = 1ull << id[0] | 1ull << id[1] | 1ull << id[2] | 1ull << id[3] | 1ull << id[4];
+#pragma unroll
+        for (int p = 0; p < P; ++p) pd[p * ld + s] = 1ull << id[5 + 2 * p] | 1ull << id[6 + 2 * p];
+    } else {
+        Dealer d(seed, env_id, episode, v.hand[s]);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) board |= 1ull << d.next();
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+            const uint64_t a = 1ull << d.next();
+            pd[p * ld + s] = a | 1ull << d.next();
+        }
+    }
+    reinterpret_cast<uint64_t*>(v.mr)[s] = board;
+}
+
+// :488-489 eval_hand(board + hole) for one seat that shows its cards
+template <class V>
+PKB_D void showdown_rank(V& v, size_t s, int seat)
+{
+    uint64_t* word = reinterpret_cast<uint64_t*>(v.pd) + seat * v.ld() + s;
+    *word = eval_mask52_sel(reinterpret_cast<const uint64_t*>(v.mr)[s] | *word);
+}
+
+template <int P, class V>
+PKB_D void showdown_settle(V& v, size_t s, const Seats& x, int npw)
 {
     const size_t ld = v.ld();
     uint32_t rk[P];
     double b[P], pay[P];
-    uint32_t todo = x.called | x.allin;  // :488, :496 seats that show their cards
-    // :488-489 eval_hand(board + hole) for CALLED / ALL_IN seats, NONE for the others
-    if constexpr (5 + 2 * P <= 13) {  // small tables: interleaved Philox blocks, sorted draw chain, select-form ranks
-        uint32_t id[5 + 2 * P];
-        deal_ids<5 + 2 * P>(seed, env_id, episode, v.hand[s], id);
-        const uint64_t board = 1ull << id[0] | 1ull << id[1] | 1ull << id[2] | 1ull << id[3] | 1ull << id[4];
+    uint32_t todo = x.called | x.allin;  // :488, :496 seats that show their cards; NONE for the others
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            // a real call: one copy of the evaluator keeps the kernel's hot code inside the instruction cache (measured)
-            const uint32_t r = eval_mask52_sel_call(board | 1ull << id[5 + 2 * p] | 1ull << id[6 + 2 * p]);
-            rk[p] = (todo >> p & 1u) ? r : PACKED_NONE;
-        }
-    } else {
-        Dealer d(seed, env_id, episode, v.hand[s]);
-        uint64_t board = 0, hole[P];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) board |= 1ull << d.next();
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            hole[p] = (1ull << d.next()) | (1ull << d.next());
-            rk[p] = PACKED_NONE;
-        }
-        // Rank only the seats that show their cards, one per trip: a warp makes as many trips as its busiest lane has
-        // showing seats (typically 2-4), not P of them with most lanes idle.
-        for (uint32_t left = todo; left; left &= left - 1) {
-            const int p = ffs32(left) - 1;
-            uint64_t h = 0;
-#pragma unroll
-            for (int q = 0; q < P; ++q) h = q == p ? hole[q] : h;
-            const uint32_t r = eval_mask52_sel_call(board | h);
-#pragma unroll
-            for (int q = 0; q < P; ++q) rk[q] = q == p ? r : rk[q];
-        }
-    }
+    for (int p = 0; p < P; ++p) rk[p] = (todo >> p & 1u) ? (uint32_t)reinterpret_cast<const uint64_t*>(v.pd)[p * ld + s] : PACKED_NONE;
     double bet0[P];  // self.bets: the order of the layers (:496) goes by the bets as they were
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         b[p] = bet0[p] = v.bt[p * ld + s];  // :485 working copy
         pay[p] = 0.0;
     }
-    int n = c.npw;
+    int n = npw;
     while (todo) {  // :496-498 seats by ascending bet, ties by seat (np.argsort, numpy 1.18.4 order)
         int p = 0;
         double least = 0.0;
@@ -591,6 +599,7 @@ PKB_D void showdown(V& v, size_t s, const Seats& x, const Ctl& c, uint64_t seed,
         v.cr[p * ld + s] += pay[p];  // :528
         v.pd[p * ld + s] = pay[p];
     }
+    v.mr[s] = 0.0;  // as end_hand's commit left it
 }
 
 // Game.end_hand, last part (game.py:530-539), then what the caller of end_hand does with its

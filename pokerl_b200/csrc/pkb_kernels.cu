@@ -59,6 +59,7 @@ struct StepArgs {
     uint32_t use_weights;
     uint32_t weights[NUM_MOVES];
     uint32_t num_tiles;
+    uint32_t strict;  // tile hand-over between launches with a release store (see epoch_publish)
 };
 
 #ifndef PKB_STRIDE_ALIGN
@@ -103,8 +104,16 @@ PKB_D bool mbar_try_wait(uint32_t bar, uint32_t parity)
 // launch with an error instead of hanging the device.
 PKB_D void mbar_wait(uint32_t bar, uint32_t parity)
 {
+#ifdef PKB_SPIN_WAIT  // measurement: poll without suspending
+    uint32_t ok = 0;
+    for (uint32_t polls = 0; !ok; ++polls) {
+        asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (polls > (1u << 26)) __trap();
+    }
+#else
     for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls)
         if (polls > (1u << 18)) __trap();
+#endif
 }
 // TMA 2-D tiled copies (SASS: UTMALDG / UTMASTG): box [rows][tile envs] <-> dense shared-memory rows
 PKB_D void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar)
@@ -118,10 +127,6 @@ PKB_D void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src_sme
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
                  "r"(src_smem)
                  : "memory");
-}
-PKB_D void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1)  // pull a box into L2 ahead of its load
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 PKB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 PKB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -148,13 +153,21 @@ PKB_D void epoch_wait(const uint32_t* word, uint32_t want)
         __nanosleep(64);
         if (polls > (1u << 22)) __trap();
     }
-    fence_async_global();  // the tile was written through the async proxy and is about to be read through it
 }
-PKB_D void epoch_publish(uint32_t* word, uint32_t value)
+// What the flag store must come after: (1) the tile's rows, written by this thread's TMA stores -- `wait_group 0` returns
+// when they have been performed (they are in L2, the GPU's point of coherence), and the proxy fence orders that before
+// the generic-proxy flag store; (2) the warp's plain stores to the caller's output arrays and the payoff plane, which the
+// next launch never reads but may overwrite.  A release store covers both formally, at the price of a GPU-scope fence
+// per tile (it waits for every store the SM has in flight: measured 1.8 us of a 38 us step).  The default therefore
+// stores the flag relaxed: (1) holds by completion, and for (2) the next writer of the same address is a warp of the
+// next launch that first has to see this flag, load the tile and run its passes -- ten microseconds behind stores that
+// are performed in one.  `strict` (PKB_STRICT_HANDOVER=1) selects the release store.
+PKB_D void epoch_publish(uint32_t* word, uint32_t value, bool strict)
 {
-    bulk_wait_all();       // this thread's TMA stores have been performed ...
-    fence_async_global();  // ... and are ordered before the generic-proxy release below
-    st_release_u32(word, value);
+    bulk_wait_all();
+    fence_async_global();
+    if (strict) st_release_u32(word, value);
+    else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(word), "r"(value) : "memory");
 }
 
 template <class L>
@@ -224,7 +237,7 @@ PKB_D void reduce_stats(const DevState& d, const Tally<P>& tl)
 }
 
 #ifdef PKB_TIMING
-__device__ unsigned long long g_wrp[4096][12];  // per warp of the last launch: start ns, end ns, SM id, 5 phase cycle sums, tiles, C/D rounds, longest C pass, max showdowns
+__device__ unsigned long long g_wrp[4096][16];  // per warp of the last launch: start ns, end ns, SM id, 5 phase cycle sums, tiles, C/D rounds, longest C pass, max showdowns
 #endif
 
 // --------------------------------------------------------------------------------------------
@@ -288,7 +301,8 @@ struct WarpTile {
     static constexpr size_t OFF_ACT = OFF_LIST_S + (size_t)T;  // u8 per slot: the caller's actions (pkb_step), fetched while the tile loads
     static constexpr size_t OFF_OUT_F = OFF_ACT + (size_t)T;    // u8 per slot: the step's flag byte ...
     static constexpr size_t OFF_OUT_V = OFF_OUT_F + (size_t)T;  // ... and valid mask, written to the caller's arrays with the tile
-    static constexpr size_t WARP_BYTES = (OFF_OUT_V + (size_t)T + 127) / 128 * 128;
+    static constexpr size_t OFF_PAIRS = OFF_OUT_V + (size_t)T;  // u16 (slot | seat << 8): the showing seats of up to 32 hands (P > 2)
+    static constexpr size_t WARP_BYTES = (OFF_PAIRS + (P > 2 ? (size_t)64 * P : 0) + 127) / 128 * 128;
     static constexpr size_t HEADER = 128;
     static constexpr size_t BYTES = HEADER + WARP_BYTES * WARPS;
     static constexpr int THREADS = 32 * WARPS;
@@ -321,6 +335,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     uint8_t* act_row = buf + L::OFF_ACT;
     uint8_t* out_f = buf + L::OFF_OUT_F;
     uint8_t* out_v = buf + L::OFF_OUT_V;
+    uint16_t* pairs = reinterpret_cast<uint16_t*>(buf + L::OFF_PAIRS);
     // whole words of the caller's output arrays can be written at once when both arrays are 4-byte aligned
     const bool out_words = ((reinterpret_cast<uintptr_t>(a.flags) | reinterpret_cast<uintptr_t>(a.valid)) & 3u) == 0;
     View<T> v = tile_view<L>(buf);
@@ -345,6 +360,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 #ifdef PKB_TIMING
     unsigned long long wt_acc[6] = {0, 0, 0, 0, 0, 0};  // cycles: load wait, pass A, pass C, pass D, store; tiles
     unsigned long long wt_rounds = 0, wt_maxc = 0, wt_maxns = 0;
+    unsigned long long wt_lw[3] = {0, 0, 0};  // load wait of a warp's first, second and later tiles
     unsigned long long wt_gt0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wt_gt0));
     long long wt_last = clock64();
@@ -362,10 +378,12 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     const uint32_t warps_total = gridDim.x * L::WARPS;
     uint32_t tile = blockIdx.x * L::WARPS + warp;
     uint32_t stored = 0xffffffffu;  // lane 0: the tile whose store is in flight and whose epoch is still to be published
+    bool handed_over = false;       // lane 0: the acquire of the coming tile's epoch has already succeeded (polled a pass early)
     for (uint32_t it = 0; tile < a.num_tiles; ++it) {
         const size_t base = (size_t)tile * T;
         if (lane == 0) {  // two TMA box copies bring the tile in, once the previous launch has stored it
-            epoch_wait(&d.epoch[tile], launch);
+            if (!handed_over) epoch_wait(&d.epoch[tile], launch);
+            fence_async_global();  // the tile was written through the async proxy and is about to be read through it
             mbar_arrive_expect_tx(bar, (uint32_t)L::BUF_BYTES);
             tma_load_2d(buf_s + (uint32_t)L::OFF_CR, &a.maps.w64, (int)base, 0, bar);
             tma_load_2d(buf_s + (uint32_t)L::OFF_META, &a.maps.u32, (int)base, 0, bar);
@@ -387,13 +405,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             }
             __syncwarp();
         }
-        mbar_wait(bar, it & 1u);
-        if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);  // its store finished long ago
-        PKB_WTICK(0);
-
-        // ---- pass A: every slot
-        uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
-        // The action draws of a lane's slots: envs whose ids differ only in bits 5-6 share a Philox block (pkb_philox.cuh),
+        // While the tile is in flight -- the action draws of a lane's slots: envs whose ids differ only in bits 5-6 share a Philox block (pkb_philox.cuh),
         // so the slots lane, lane+32, ... of a tile need the block of the 128-aligned id group the tile starts in and,
         // if the tile runs past that group's end, the next group's: one or two blocks per lane and tile instead of one
         // per slot (tiles of up to 160 envs span at most two groups).
@@ -413,6 +425,17 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             for (int k = 0; k < NQ; ++k)  // slot k takes word first + k of the two blocks (compile-time indices only: registers)
                 queue[k] = first == 0 ? w8[k & 7] : first == 1 ? w8[(k + 1) & 7] : first == 2 ? w8[(k + 2) & 7] : w8[(k + 3) & 7];
         }
+        // The previous tile's store was issued just before this tile's load: waiting for it to be performed and releasing
+        // its epoch (a GPU-scope fence) costs about what the load takes, and the warp has nothing else to do until then.
+        if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u, a.strict != 0);
+        mbar_wait(bar, it & 1u);
+#ifdef PKB_TIMING
+        wt_lw[it < 2 ? it : 2] += (unsigned long long)(clock64() - wt_last);
+#endif
+        PKB_WTICK(0);
+
+        // ---- pass A: every slot
+        uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
         const uint32_t n_live = d.n - base < (size_t)T ? (uint32_t)(d.n - base) : (uint32_t)T;  // slots of this tile that are envs
         PKB_UNROLL(PKB_WT_UNROLL_A)
         for (int s = lane; s < T; s += 32) {
@@ -428,7 +451,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 if (SAMPLE) {
                     const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
-                    if (a.actions_out) a.actions_out[env] = action;
+                    act_row[s] = (uint8_t)action;  // pkb_step_random(actions_out): copied out with the tile's outputs
                 } else {
                     action = act_row[s];
                     action = action == 255 ? ACTION_SKIP : action;
@@ -461,14 +484,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         }
         __syncwarp();
         PKB_WTICK(1);
-#ifndef PKB_WT_NO_PREFETCH
-        // The next tile is known by now (the dispenser answered during pass A): start it on its way into L2, so
-        // that the load after this tile's stores finds it there instead of waiting on HBM with the buffer empty.
-        if (lane == 0 && next < a.num_tiles) {
-            const int nb = (int)(next * (uint32_t)T);
-            tma_prefetch_2d(&a.maps.w64, nb, 0);  // the 8-byte rows are 85 % of the tile; the rest rides on the load itself
-        }
-#endif
+        // the previous tile's store has had pass A's time to finish: publish it without waiting
+        // one look at the next tile's epoch while passes C and D run: the acquire's round trip is off the load's path
+        if (lane == 0) handed_over = next < a.num_tiles && ld_acquire_u32(&d.epoch[next]) == launch;
 
         // Passes C and D repeat while hands keep ending inside this step (all-in blinds: a slot whose next hand
         // cannot be acted on either); such slots go round again through the SAME code, side by side.
@@ -478,13 +496,39 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             wt_rounds += 1;
             wt_maxns = n_s > wt_maxns ? n_s : wt_maxns;
 #endif
-            // ---- pass C: the ranked showdown for the slots in list S
-            for (uint32_t i = lane; i < n_s; i += 32) {
-                const int s = list_s[i];
-                const Seats x = load_seats<P>(v, s);
-                Ctl c{PC_SHOWDOWN, 0, 0, 0, 0, 0, 0, popc32(x.active | x.called | x.allin)};
-                ++tl.shows;
-                showdown<P>(v, s, x, c, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+            // ---- pass C: the ranked showdown for the slots in list S, 32 hands at a time, in three phases that each keep
+            // the lanes busy with their own kind of work item (pkb_game.cuh): deal per hand, rank per (hand, seat), pots per hand
+            for (uint32_t i0 = 0; i0 < n_s; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool have = i < n_s;
+                int s = 0;
+                Seats x{0, 0, 0, 0};
+                if (have) {
+                    s = list_s[i];
+                    x = load_seats<P>(v, s);
+                    ++tl.shows;
+                    showdown_deal<P>(v, s, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+                }
+                if constexpr (P == 2) {  // both seats of every hand: lane pairs
+                    __syncwarp();
+                    const uint32_t hands = n_s - i0 < 32u ? n_s - i0 : 32u;
+                    for (uint32_t j = lane; j < 2u * hands; j += 32) showdown_rank(v, list_s[i0 + (j >> 1)], (int)(j & 1u));
+                } else {  // the seats that show their cards (game.py:488), listed hand by hand
+                    const uint32_t todo = x.called | x.allin;
+                    uint32_t upto = (uint32_t)popc32(todo);  // inclusive prefix sum over the lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(FULL, upto, o);
+                        upto += lane >= o ? y : 0u;
+                    }
+                    const uint32_t total = __shfl_sync(FULL, upto, 31);
+                    uint32_t at = upto - (uint32_t)popc32(todo);
+                    for (uint32_t left = todo; left; left &= left - 1) pairs[at++] = (uint16_t)((uint32_t)s | (uint32_t)(ffs32(left) - 1) << 8);
+                    __syncwarp();
+                    for (uint32_t j = lane; j < total; j += 32) showdown_rank(v, pairs[j] & 255u, (int)(pairs[j] >> 8));
+                }
+                __syncwarp();
+                if (have) showdown_settle<P>(v, s, x, popc32(x.active | x.called | x.allin));
             }
             __syncwarp();
             PKB_WTICK(2);
@@ -550,6 +594,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
         fence_async_smem();
         __syncwarp();
+        if (SAMPLE && a.actions_out)
+            for (int s = lane; s < T && base + s < d.n; s += 32) a.actions_out[base + s] = act_row[s];
         if (out_words && base + T <= d.n) {  // the two output rows: one 32-bit store per lane and 32 slots
 #pragma unroll
             for (int w = lane; w < T / 4; w += 32) {
@@ -577,7 +623,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         wt_acc[5] += 1;
 #endif
     }
-    if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
+    if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u, a.strict != 0);
 #ifdef PKB_TIMING
     {
         const uint32_t gw = blockIdx.x * L::WARPS + warp;
@@ -593,6 +639,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             g_wrp[gw][9] = wt_rounds;
             g_wrp[gw][10] = wt_maxc;
             g_wrp[gw][11] = wt_maxns;
+            for (int i = 0; i < 3; ++i) g_wrp[gw][12 + i] = wt_lw[i];
         }
     }
 #endif
@@ -1077,7 +1124,7 @@ extern "C" {
 
 #ifdef PKB_TIMING
 // debug builds only: the per-warp timeline of the last step launch (profiles/warp_timing.py)
-int pkb_debug_warps(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_wrp, sizeof(unsigned long long) * 4096 * 12) == cudaSuccess ? 0 : -1; }
+int pkb_debug_warps(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_wrp, sizeof(unsigned long long) * 4096 * 16) == cudaSuccess ? 0 : -1; }
 #endif
 
 const char* pkb_last_error(void) { return g_error.c_str(); }
@@ -1229,6 +1276,8 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.valid = valid;
     a.step_idx = step_idx;
     a.use_weights = weights ? 1u : 0u;
+    static const bool strict = getenv("PKB_STRICT_HANDOVER") != nullptr && getenv("PKB_STRICT_HANDOVER")[0] == '1';
+    a.strict = strict ? 1u : 0u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PKB_CUDA(order_on_stream(h, s));

@@ -19,13 +19,15 @@ for t in range(20):
     g.step_random(t)
 torch.cuda.synchronize()
 L = C.CDLL(os.environ["PKB_LIB"])
+CHAIN = int(os.environ.get("PKB_TIMING_CHAIN", "1"))  # > 1: that many back-to-back launches (pipelined); the table shows the last
 for rep in range(3):
     flush.zero_()
-    g.step_random(99 + rep)
+    for k in range(CHAIN):
+        g.step_random(99 + rep * CHAIN + k)
     torch.cuda.synchronize()
-    buf = (C.c_ulonglong * (4096 * 12))()
+    buf = (C.c_ulonglong * (4096 * 16))()
     L.pkb_debug_warps(buf)
-    W = np.array(list(buf), dtype=np.int64).reshape(4096, 12)
+    W = np.array(list(buf), dtype=np.int64).reshape(4096, 16)
     W = W[W[:, 1] > 0]
     t0 = W[:, 0].min()
     end = (W[:, 1] - t0) / 1e3
@@ -48,6 +50,8 @@ for rep in range(3):
     tot = W[:, 3:8].sum()
     for i, n in enumerate(names):
         print(f"   {n:10s} {W[:, 3 + i].sum() / tiles:8.0f} cycles per tile ({100 * W[:, 3 + i].sum() / tot:4.1f}%)")
+    cnt = np.minimum(W[:, 8], 1).sum(), np.minimum(np.maximum(W[:, 8] - 1, 0), 1).sum(), np.maximum(W[:, 8] - 2, 0).sum()
+    print("   load wait by round (cycles per tile): first %.0f second %.0f later %.0f" % tuple(W[:, 12 + i].sum() / max(1, cnt[i]) for i in range(3)))
     order = np.argsort(-end)[:6]
     print("   slowest warps (end us, sm, tiles, cycles A/C/D, C/D rounds, longest C pass, max showdowns):",
           [(round(float(end[i]), 1), int(W[i, 2]), int(W[i, 8]), int(W[i, 4]), int(W[i, 5]), int(W[i, 6]), int(W[i, 9]), int(W[i, 10]), int(W[i, 11])) for i in order])
