@@ -2,25 +2,29 @@
 """bench.py -- env-steps/s (+ 7-card hand-evals/s) of the pokerl hot path on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--gpus N] ...                # the CPU comparator (oracle port)
+    python bench.py --impl reference [--gpus N] ...                # the unmodified reference on the host cores
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # N > 1: one rank per GPU
 
-Workload (BASELINE.json configs[2]): heads-up NLHE, 2^20 lockstep envs PER GPU, start_credits 100, blinds
-2/1, uniform random agents drawn on device from Philox(seed 0, global env id, step), auto-reset on
-game over.  One bench "step" = one Game.step on every env = one launch of the fused
-sample+step kernel (pkb::step_warp_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective
-(weak scaling); one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
+Headline workload (BASELINE.json configs[2]): heads-up NLHE, 2^20 lockstep envs PER GPU, start_credits 100, blinds
+2/1, uniform random agents drawn on device from Philox(seed 0, global env id, step), auto-reset on game over.  One
+bench "step" = one Game.step on every env of one batch = ONE launch of the fused sample+step kernel
+(pkb::step_warp_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective (weak scaling);
+one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
 
-Timing: W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket, timed with
-one CUDA event pair; the reported time is the max over ranks.  One 2^20-env batch (96 MB of state)
-would fit the 126 MB L2, so each GPU holds THREE such batches (289 MB, "inputs larger than L2") and
-steps them round-robin: every step is one pass of the hot path over one batch of 2^20 envs whose
-state was pushed out of L2 by the steps of the other two batches, i.e. it streams from HBM and back.
-The batches are independent, so each one is stepped on its own CUDA stream: the drain of one step's
-persistent kernel (a few tiles whose envs play several hands inside one step) overlaps the next
-batch's step.  `value` is that whole-job throughput; `roofline.isolated_launch_us` is the duration of
-one step launched alone on one stream (the same three batches, one stream), and `flushed_by_memset` /
-`l2_resident` give the single-batch variants for reference.
+Timing: every batch is first rolled PREROLL steps forward (untimed set-up) so that the timed steps meet the
+steady-state mix of streets, hand ends and showdowns instead of 2^20 tables that were all dealt at the same moment;
+then W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket, timed with one CUDA event
+pair; the reported time is the max over ranks.  One 2^20-env batch (92 MB of state) would fit the 126 MB L2, so each
+GPU holds THREE such batches ("inputs larger than L2") and steps them round-robin on ONE stream: every step is one
+pass of the hot path over one batch whose state was pushed out of L2 by the steps of the other two, i.e. it streams
+from HBM and back.  Consecutive step launches of a stream overlap inside the library (programmatic dependent launch
+with a per-tile hand-over): `ms_per_step` is the launch INTERVAL of that pipeline, and
+`roofline.unpipelined_launch_us` is the duration of one launch with nothing else on the GPU.
+
+The same JSON line carries BASELINE.json configs[3] (`nine_player`: 2^22 global envs sharded over the ranks, unequal
+stacks, all-in heavy action mix) and configs[4] (`q_learning`: the batched q-learning example, 2^26 global envs with
+the NCCL Q-delta reduction), the 7-card evaluator (`hand_evals`), and the CPU baselines: the unmodified reference
+(baseline/_ref, one process per host core) and this repo's C port of it (oracle/).
 
 Prints ONE JSON line on rank 0.
 """
@@ -38,9 +42,14 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(num_players=2, start_credits=100, big_blind=2, small_blind=1, seed=0)
 ENVS_PER_GPU = 1 << 20
-RESIDENT_BATCHES = 3  # 3 x 96 MB of env state per GPU: larger than the 126 MB L2
-E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "6"))       # env batches the end-to-end leg keeps in flight (a batch's step waits for its own copies)
+RESIDENT_BATCHES = 3  # 3 x 92 MB of env state per GPU: larger than the 126 MB L2
+PREROLL = 64          # untimed steps every batch is rolled forward before anything is measured (steady-state hand mix)
+E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "6"))  # env batches the end-to-end leg keeps in flight
 L2_FLUSH_BYTES = 256 << 20
+NINE = dict(num_players=9, start_credits=[20 * (i + 1) for i in range(9)], big_blind=2, small_blind=1, seed=1,
+            weights=[10, 30, 30, 5, 5, 5, 45], global_envs=1 << 22)  # BASELINE.json configs[3] / SURVEY 8(d)
+QL = dict(num_players=4, global_envs=1 << 26)                        # BASELINE.json configs[4]
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def algorithmic_bytes_per_step(P: int) -> int:
@@ -57,7 +66,7 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(key: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
     except Exception:
@@ -112,9 +121,98 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU comparator: the oracle port, all host threads (the reference itself is pure Python and does
-# not exist on the GPU box; see DESIGN.md "CPU baseline")
+# CPU baselines.  (1) The UNMODIFIED reference (pure Python + numpy, installed under baseline/_ref):
+# one Game per process, one process per host core, the loop of examples/random_game.py with
+# auto-reset.  (2) This repo's C port of the same loop (oracle/pokerl_oracle.c, OpenMP).
 # ------------------------------------------------------------------------------------------------
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _reference_worker(job):
+    """One process: the reference's Game.step loop with uniform-random valid actions for `seconds`."""
+    P, seconds, seed = job
+    import logging
+    import random
+    import signal
+    sys.path.insert(0, REF_DIR)
+    import numpy as np
+    from pokerl import Game  # the unmodified reference (pokerl/game.py)
+    logging.disable(logging.CRITICAL)
+    random.seed(seed)
+    np.random.seed(seed)
+
+    class _Stuck(Exception):
+        pass
+
+    def on_alarm(*_):
+        raise _Stuck()
+
+    # the reference's `while` at game.py:607 has no termination guarantee: never let a worker outlive the sample
+    signal.signal(signal.SIGALRM, on_alarm)
+    signal.setitimer(signal.ITIMER_REAL, seconds + 3.0)
+    game = Game(num_players=P, start_credits=100, big_blind=2, small_blind=1)
+    game.reset()
+    steps, in_step, stuck = 0, 0.0, 0
+    clock = time.perf_counter
+    t0 = clock()
+    try:
+        while True:
+            now = clock()
+            if now - t0 >= seconds:
+                break
+            try:
+                state = game.active_state                                   # StateView construction + get_valid_actions
+                action = int(np.random.choice(list(state.valid_action_indices)))  # examples/random_game.py:8
+                t1 = clock()
+                done, *_ = game.step(action)                                # game.py:621-700
+                in_step += clock() - t1
+                steps += 1
+                if done:
+                    game.reset()
+            except AssertionError:  # game.py:473
+                stuck += 1
+                game.reset()
+    except _Stuck:
+        stuck += 1
+    signal.setitimer(signal.ITIMER_REAL, 0)
+    return steps, in_step, clock() - t0, stuck
+
+
+def reference_rate(P: int, seconds: float, cores: int) -> dict:
+    """env-steps/s of the unmodified reference over `cores` processes (full loop and Game.step-only)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")  # the parent may hold a CUDA context
+    with ctx.Pool(cores) as pool:
+        res = pool.map_async(_reference_worker, [(P, seconds, 1000 * P + i) for i in range(cores)]).get(timeout=seconds + 60)
+    steps = sum(r[0] for r in res)
+    wall = max(r[2] for r in res)
+    return {"num_players": P, "value": steps / wall, "unit": "env-steps/s", "cores": cores,
+            "per_core": steps / wall / cores, "step_only_per_core": statistics.mean(r[0] / r[1] for r in res if r[1] > 0),
+            "steps": steps, "seconds": wall, "stuck_or_asserting_games": sum(r[3] for r in res)}
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REF_DIR, "pokerl"))
+
+
+def cpu_baseline_reference(seconds=5.0, players=(2, 4, 9)) -> dict:
+    cores = os.cpu_count() or 1
+    runs = {str(P): reference_rate(P, seconds, cores) for P in players}
+    head = runs[str(WORKLOAD["num_players"])]
+    return {"value": head["value"], "unit": "env-steps/s", "cores": cores, "kind": "reference", "cpu_model": cpu_model(),
+            "sample": f"unmodified sneppy/pokerl 0.0.6 (baseline/_ref): one Game per process, {cores} processes, "
+                      f"uniform-random valid actions through Game.active_state, auto-reset on game over, "
+                      f"{head['seconds']:.1f} s per table size; value = heads-up full loop",
+            "by_num_players": runs}
+
 
 def use_all_host_threads(ora):
     """torchrun exports OMP_NUM_THREADS=1; the CPU comparator is meant to use every host core."""
@@ -123,22 +221,18 @@ def use_all_host_threads(ora):
     return cores
 
 
-def cpu_rate_probe(ora, P):
-    b = ora.OracleBatch(1 << 14, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
-                        seed=WORKLOAD["seed"], auto_reset=True)
-    b.reset()
-    b.run_random(0, 8)
-    t0 = time.perf_counter()
-    n = b.run_random(8, 32)
-    return n / (time.perf_counter() - t0)
-
-
-def cpu_baseline(target_seconds=12.0) -> dict:
-    """Oracle port timed on a bounded sample of the same workload (rank 0, N=1 only)."""
+def cpu_baseline_port(target_seconds=8.0) -> dict:
+    """Oracle port timed on a bounded sample of the same workload."""
     from oracle import pyoracle as ora
     P = WORKLOAD["num_players"]
     cores = use_all_host_threads(ora)
-    rate = cpu_rate_probe(ora, P)
+    probe = ora.OracleBatch(1 << 14, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
+                            seed=WORKLOAD["seed"], auto_reset=True)
+    probe.reset()
+    probe.run_random(0, 8)
+    t0 = time.perf_counter()
+    n = probe.run_random(8, 32)
+    rate = n / (time.perf_counter() - t0)
     envs = 1 << 16
     steps = max(16, min(4096, int(rate * target_seconds / envs)))
     b = ora.OracleBatch(envs, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
@@ -148,41 +242,30 @@ def cpu_baseline(target_seconds=12.0) -> dict:
     t0 = time.perf_counter()
     n = b.run_random(4, steps)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+    return {"value": n / dt, "unit": "env-steps/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
             "sample": f"{envs} envs x {steps} steps of the same heads-up random-agent workload "
                       f"(oracle/pokerl_oracle.c, OpenMP over {cores} host threads, {dt:.1f} s)"}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path on the host cores, same metric/config."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same metric/config."""
     if rank != 0:
         return
-    from oracle import pyoracle as ora
-    P = WORKLOAD["num_players"]
-    cores = use_all_host_threads(ora)
-    rate = cpu_rate_probe(ora, P)
-    total_steps = args.steps + args.warmup
-    # bounded sample: as many envs (<= the full 2^20) as keep the whole run near one minute
-    envs = ENVS_PER_GPU
-    while envs > 4096 and envs * total_steps / rate > 60.0:
-        envs //= 2
-    b = ora.OracleBatch(envs, P, WORKLOAD["start_credits"], WORKLOAD["big_blind"], WORKLOAD["small_blind"],
-                        seed=WORKLOAD["seed"], auto_reset=True)
-    b.reset()
-    b.run_random(0, args.warmup)
-    t0 = time.perf_counter()
-    n = b.run_random(args.warmup, args.steps)
-    dt = time.perf_counter() - t0
-    value = n / dt
+    seconds = float(os.environ.get("PKB_BENCH_REF_SECONDS", "6"))
+    port = cpu_baseline_port()
+    if reference_available():
+        base = cpu_baseline_reference(seconds)
+    else:  # the reference install did not travel: fall back to the port and say so
+        base = dict(port, sample=port["sample"] + " [baseline/_ref missing: the C port stands in for the reference]")
+    value = base["value"]
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ENVS_PER_GPU / value * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(envs, world, note="CPU comparator on a bounded sample of the workload"),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{envs} envs x {args.steps} steps (oracle/pokerl_oracle.c port of the reference's "
-                                   f"Game.step loop, OpenMP over {cores} host threads; the reference itself is pure "
-                                   f"Python and is not present on the GPU box)"},
+        "config": workload_config(ENVS_PER_GPU, world, note="CPU arm: each timed sample is a bounded run of the same "
+                                  "workload (tables stepped for a fixed time per process); ms_per_step = the time one "
+                                  "2^20-env step would take at the measured rate"),
+        "cpu_baseline": base, "cpu_baseline_port": port,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,9 +278,12 @@ def workload_config(envs_per_gpu, world, note=None):
            "blinds": [WORKLOAD["big_blind"], WORKLOAD["small_blind"]], "agents": "uniform random over valid actions, on device",
            "auto_reset": True, "seed": WORKLOAD["seed"], "sharding": f"env-sliced x{world}, no data-path collective",
            "resident_batches_per_gpu": RESIDENT_BATCHES,
+           "preroll_steps": PREROLL,
+           "preroll": f"every batch is stepped {PREROLL} times before warm-up (untimed set-up): steady-state mix of streets, "
+                      "hand ends and showdowns",
            "l2": f"inputs larger than L2: {RESIDENT_BATCHES} batches of {envs_per_gpu} envs per GPU "
-                 f"({RESIDENT_BATCHES * 96 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2) stepped round-robin, "
-                 "one batch per step"}
+                 f"({RESIDENT_BATCHES * 92 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2) stepped round-robin on one "
+                 "stream, one batch per step"}
     if note:
         cfg["note"] = note
     return cfg
@@ -212,13 +298,14 @@ def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     from pokerl_b200 import GameBatch
     from pokerl_b200 import _native as nat
-    from pokerl_b200.judger import eval_masks_batch, random_hands
+    from pokerl_b200.judger import random_hands
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     nat.require_cuda()
     P, N = WORKLOAD["num_players"], args.envs
     K, W = args.steps, args.warmup
+    peak, peak_src = measured_peak_gbs()
 
     def make_batch(j=0):
         # global env ids: every batch of every rank has its own contiguous slice
@@ -231,66 +318,48 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn):
+        """Device time (ms) of fn() between a barrier + synchronize on both sides."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        fn()
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
+
     batches = [make_batch(j) for j in range(RESIDENT_BATCHES)]
     for g in batches:
         g.reset()
     t_idx = 0  # step index of the device-side random agents (per batch it only has to be distinct per step)
 
-    def step_next():
+    def run_steps(n):
+        """n steps round-robin over the resident batches, one launch each, all on the current stream."""
         nonlocal t_idx
-        batches[t_idx % RESIDENT_BATCHES].step_random(t_idx)  # ONE launch: fused sampler + Game.step on N envs
-        t_idx += 1
+        for _ in range(n):
+            batches[t_idx % RESIDENT_BATCHES].step_random(t_idx)  # ONE launch: fused sampler + Game.step on N envs
+            t_idx += 1
 
-    for _ in range(max(W, RESIDENT_BATCHES)):
-        step_next()
+    run_steps(PREROLL * RESIDENT_BATCHES)  # untimed set-up: the steady-state hand mix
+    run_steps(max(W, RESIDENT_BATCHES))    # warm-up
     torch.cuda.synchronize()
     for g in batches:
         g.stats_reset()
 
-    main = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(RESIDENT_BATCHES)]
-
-    def run_steps(n, overlapped):
-        """n steps round-robin over the resident batches; overlapped: one stream per batch, joined at the end."""
-        nonlocal t_idx
-        if overlapped:
-            for st in streams:
-                st.wait_stream(main)
-        for _ in range(n):
-            j = t_idx % RESIDENT_BATCHES
-            if overlapped:
-                with torch.cuda.stream(streams[j]):
-                    batches[j].step_random(t_idx)
-            else:
-                batches[j].step_random(t_idx)
-            t_idx += 1
-        if overlapped:
-            for st in streams:
-                main.wait_stream(st)
-
-    run_steps(2 * RESIDENT_BATCHES, True)
-    torch.cuda.synchronize()
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    barrier()
     wall0 = time.perf_counter()
-    e_start.record()
-    run_steps(K, True)
-    e_stop.record()
-    barrier()
+    dev_ms = timed(lambda: run_steps(K))
     wall = time.perf_counter() - wall0
     clock_info = clocks.stop() if rank == 0 else None
-    dev_ms = e_start.elapsed_time(e_stop)
-    # the same K steps on ONE stream: every launch alone on the GPU (the kernel's own duration)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    run_steps(K, False)
-    e1.record()
-    torch.cuda.synchronize()
-    isolated_ms = e0.elapsed_time(e1) / K
+
+    # the same K steps with plain stream order between launches: every launch alone on the GPU (the kernel's own duration)
+    for g in batches:
+        g.set_pipelining(False)
+    unpipelined_ms = timed(lambda: run_steps(K)) / K
+    for g in batches:
+        g.set_pipelining(True)
     stats = batches[0].stats()
     for g in batches[1:]:
         sj = g.stats()
@@ -298,36 +367,22 @@ def run_ours(args, rank, local_rank, world):
             stats[k] += sj[k]
         stats["payoff_sum"] = [a + b for a, b in zip(stats["payoff_sum"], sj["payoff_sum"])]
 
-    # ---- for reference: one batch, L2 flushed by a 256 MB memset before every step (each step timed on its own)
+    # ---- for reference: ONE batch stepped back to back (its 92 MB of state stays in the 126 MB L2)
     g = batches[0]
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     KF = min(K, 64)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
-    barrier()
-    for i in range(KF):
-        flush.zero_()
-        starts[i].record()
-        g.step_random(t_idx + i)
-        stops[i].record()
-    torch.cuda.synchronize()
-    flushed_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops)) / KF
-    # ---- and the same batch back to back without any flush (its state stays in the 126 MB L2)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(KF):
-        g.step_random(t_idx + KF + i)
-    e1.record()
-    torch.cuda.synchronize()
-    resident_ms = e0.elapsed_time(e1) / KF
-    del flush
+
+    def one_batch():
+        for i in range(KF):
+            g.step_random(t_idx + i)
+    resident_ms = timed(one_batch) / KF
 
     # ---- end to end through the public API with HOST buffers.  Every step: H2D copy of that step's actions from
-    # pinned host memory, GameBatch.step, D2H copy of its flags and valid masks.  As in the device-resident leg, the
-    # independent resident batches take turns, each on its own stream, so one batch's copies overlap another batch's
-    # step (a caller that keeps several env batches in flight does exactly this; within a batch, copy-in -> step ->
-    # copy-out is a serial chain, so E2E_BATCHES of them are in flight); the actions are a recording of the
-    # device-side random agents, so every one of them is valid for the state it meets.
+    # pinned host memory, GameBatch.step, D2H copy of its flags and valid masks.  Independent batches take turns, each
+    # on its own stream, so one batch's copies overlap another batch's step (a caller that keeps several env batches
+    # in flight does exactly this; within a batch, copy-in -> step -> copy-out is a serial chain, so E2E_BATCHES of
+    # them are in flight); the actions are a recording of the device-side random agents, so every one of them is
+    # valid for the state it meets.
+    main = torch.cuda.current_stream(dev)
     R = max(1, min(K, 126) // E2E_BATCHES)  # rounds; E = R * E2E_BATCHES steps
     E = R * E2E_BATCHES
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(E2E_BATCHES)]
@@ -336,14 +391,18 @@ def run_ours(args, rank, local_rank, world):
         rec = make_batch(j)
         rec.reset()
         ha = torch.empty((R, N), dtype=torch.uint8).pin_memory()  # one byte per action (pkb_step_u8)
+        for r in range(PREROLL):
+            rec.step_random(r)
         for r in range(R):
-            rec.step_random(r, record_actions=True)
+            rec.step_random(PREROLL + r, record_actions=True)
             ha[r].copy_(rec.actions_taken.to(torch.uint8))
         torch.cuda.synchronize()
         del rec
         host_actions.append(ha)
         run = make_batch(j)
         run.reset()
+        for r in range(PREROLL):
+            run.step_random(r)
         runs.append(run)
     dev_actions = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(E2E_BATCHES)]
     host_out = [torch.empty((2, N), dtype=torch.uint8).pin_memory() for _ in range(E2E_BATCHES)]  # flags, valid
@@ -362,55 +421,88 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t0
     rejected = sum(run.stats()["invalid"] for run in runs)
     assert rejected == 0, f"e2e replay produced {rejected} rejected actions"
-    del runs
+    del runs, batches, g
+
+    # ---- BASELINE.json configs[3]: nine players, unequal stacks, all-in heavy mix, 2^22 GLOBAL envs sharded over the ranks
+    from pokerl_b200 import distributed as D
+    base9, n9 = D.shard_envs(NINE["global_envs"], rank, world)
+    g9 = GameBatch(n9, NINE["num_players"], NINE["start_credits"], NINE["big_blind"], NINE["small_blind"],
+                   seed=NINE["seed"], env_id_base=base9, auto_reset=True, device=local_rank)
+    g9.reset()
+    for t in range(32 + max(W, 3)):
+        g9.step_random(t, NINE["weights"])
+    K9 = max(4, min(K, 64))
+    g9.stats_reset()
+
+    def nine_steps():
+        for i in range(K9):
+            g9.step_random(1000 + i, NINE["weights"])
+    nine_ms = timed(nine_steps)
+    g9.set_pipelining(False)
+    nine_unpipelined_ms = timed(nine_steps) / K9
+    s9 = g9.stats()
+    del g9
 
     # ---- 7-card hand evals/s on random hands resident in HBM (12 B per eval: 8 in, 4 out)
     n_hands = 1 << 27
     masks = random_hands(0, n_hands, device=dev)
     out = torch.empty(n_hands, dtype=torch.int32, device=dev)
-    from pokerl_b200 import _native as _n
     stream = torch.cuda.current_stream(dev).cuda_stream
     for _ in range(3):
-        _n.check(_n.lib().pkb_eval_masks(_n.ptr(masks), n_hands, _n.ptr(out), stream))
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nat.check(nat.lib().pkb_eval_masks(nat.ptr(masks), n_hands, nat.ptr(out), stream))
     reps = 5
-    ev0.record()
-    for _ in range(reps):
-        _n.check(_n.lib().pkb_eval_masks(_n.ptr(masks), n_hands, _n.ptr(out), stream))
-    ev1.record()
-    torch.cuda.synchronize()
-    eval_ms = ev0.elapsed_time(ev1) / reps
+
+    def evals():
+        for _ in range(reps):
+            nat.check(nat.lib().pkb_eval_masks(nat.ptr(masks), n_hands, nat.ptr(out), stream))
+    eval_ms = timed(evals) / reps
     del masks, out
 
+    # ---- BASELINE.json configs[4]: the batched q-learning example, 2^26 GLOBAL envs, NCCL Q-delta reduction per step
+    ql = None
+    if not args.no_q_learning:
+        ql = q_learning_block(args, rank, local_rank, world, timed)
+
     # ---- max over ranks; NCCL reduction of the statistics vector (the only collective)
-    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, flushed_ms, isolated_ms], dtype=torch.float64, device=dev)
+    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms],
+                       dtype=torch.float64, device=dev)
     svec = torch.tensor([stats["steps"], stats["hands"], stats["showdowns"], stats["games"], stats["invalid"],
                          stats["poisoned"]] + stats["payoff_sum"], dtype=torch.float64, device=dev)
+    s9vec = torch.tensor([s9["steps"], s9["hands"], s9["showdowns"], s9["games"], s9["invalid"], s9["poisoned"]],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(svec, op=dist.ReduceOp.SUM)
-    dev_ms, resident_ms, e2e_s, eval_ms, flushed_ms, isolated_ms = vec.tolist()
+        dist.all_reduce(s9vec, op=dist.ReduceOp.SUM)
+    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms = vec.tolist()
     if rank != 0:
         return
 
-    peak, peak_src = measured_peak_gbs()
     bytes_per_launch = algorithmic_bytes_per_step(P) * N
     avg_launch_s = dev_ms / K / 1e3
     achieved = bytes_per_launch / avg_launch_s / 1e9
     value = N * world * K / (dev_ms / 1e3)
     eval_rate = n_hands * world / (eval_ms / 1e3)
+    b9 = algorithmic_bytes_per_step(NINE["num_players"])
+    nine_rate = NINE["global_envs"] * K9 / (nine_ms / 1e3)
+    nine_gbs = b9 * (NINE["global_envs"] / world) * K9 / (nine_ms / 1e3) / 1e9  # per GPU
     line = {
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(N, world),
         "roofline": {"bound": "hbm", "kernel": "pkb::step_warp_kernel<2,true>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("step_kernel_p2"),
+                     "traffic_note": ncu_traffic("step_kernel_p2_note"),
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_step(P),
                      "bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
-                     "avg_launch_note": "timed region / launches; the launches of the three resident batches run on three streams and overlap",
-                     "isolated_launch_us": isolated_ms * 1e3, "isolated_achieved": bytes_per_launch / (isolated_ms / 1e3) / 1e9,
-                     "isolated_frac": bytes_per_launch / (isolated_ms / 1e3) / 1e9 / peak, "peak_source": peak_src},
+                     "avg_launch_note": "timed region / launches on ONE stream; consecutive launches overlap inside the library "
+                                        "(programmatic dependent launch, tiles handed over one by one), so this is the launch "
+                                        "interval of the pipeline, ramp-up and drain of the timed region included",
+                     "unpipelined_launch_us": unpipelined_ms * 1e3,
+                     "unpipelined_achieved": bytes_per_launch / (unpipelined_ms / 1e3) / 1e9,
+                     "unpipelined_frac": bytes_per_launch / (unpipelined_ms / 1e3) / 1e9 / peak,
+                     "unpipelined_note": "pkb_set_pipelining(0): every launch alone on the GPU, its tail not overlapped",
+                     "peak_source": peak_src},
         "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": N,
                 "d2h_bytes_per_step": 2 * N, "steps": E,
                 "path": "per step: one byte per action H2D from pinned host -> GameBatch.step -> pkb_step_u8 -> flags+valid D2H (one copy) to pinned host; "
@@ -418,10 +510,19 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": K,  # one persistent step_warp_kernel launch per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",
-                        "note": "one batch stepped back to back: its 96 MB of state stays in the 126 MB L2"},
-        "flushed_by_memset": {"value": N * world / (flushed_ms / 1e3), "unit": "env-steps/s", "us_per_step": flushed_ms * 1e3,
-                              "note": "one batch, 256 MB memset before every step, each step timed on its own: the step "
-                                      "also pays for writing the memset's dirty lines out of L2"},
+                        "frac": bytes_per_launch / (resident_ms / 1e3) / 1e9 / peak,
+                        "note": "ONE batch stepped back to back on one stream: its 92 MB of state stays in the 126 MB L2"},
+        "nine_player": {"metric": "env_steps_per_sec", "value": nine_rate, "unit": "env-steps/s", "steps": K9,
+                        "ms_per_step": nine_ms / K9, "scaling": "strong",
+                        "config": {"workload": "9-player NLHE, all-in / side-pot heavy mix (BASELINE.json configs[3])",
+                                   "num_players": 9, "global_envs": NINE["global_envs"], "envs_per_gpu": NINE["global_envs"] // world,
+                                   "start_credits": NINE["start_credits"], "weights_fold_check_call_r10_r25_r50_allin": NINE["weights"],
+                                   "seed": NINE["seed"], "auto_reset": True, "preroll_steps": 32,
+                                   "l2": "inputs larger than L2 at 1-2 GPUs (1.3 GB of state); one handle per GPU"},
+                        "roofline": {"bound": "hbm", "kernel": "pkb::step_warp_kernel<9,true>", "achieved": nine_gbs, "peak": peak,
+                                     "unit": "GB/s", "frac": nine_gbs / peak, "algorithmic_bytes_per_env_step": b9,
+                                     "unpipelined_launch_us": nine_unpipelined_ms * 1e3, "traffic": ncu_traffic("step_kernel_p9")},
+                        "stats": dict(zip(("steps", "hands", "showdowns", "games", "invalid", "poisoned"), s9vec.tolist()))},
         "hand_evals": {"metric": "hand_evals_per_sec", "value": eval_rate, "unit": "7-card evals/s", "hands": n_hands,
                        "roofline": {"bound": "hbm", "kernel": "pkb::eval_masks_hash_kernel", "achieved": 12 * eval_rate / world / 1e9,
                                     "peak": peak, "unit": "GB/s", "frac": 12 * eval_rate / world / 1e9 / peak,
@@ -431,9 +532,27 @@ def run_ours(args, rank, local_rank, world):
                   "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},
         "wall_s_timed_region": wall,
     }
+    if ql is not None:
+        line["q_learning"] = ql
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
+        port = cpu_baseline_port()
+        if reference_available():
+            line["cpu_baseline"] = cpu_baseline_reference(float(os.environ.get("PKB_BENCH_REF_SECONDS", "5")))
+            line["cpu_baseline_port"] = port
+        else:
+            line["cpu_baseline"] = port
     print(json.dumps(line), flush=True)
+
+
+def q_learning_block(args, rank, local_rank, world, timed):
+    """BASELINE.json configs[4]: examples/q_learning.py batched to 2^26 global envs with the NCCL Q-delta reduction."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pkb_q_learning", os.path.join(ROOT, "examples", "q_learning.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    # 2^23 tables per GPU: the full 2^26 of configs[4] on eight GPUs, the same per-GPU share on fewer
+    return mod.bench_block(QL["global_envs"] // 8, rank, local_rank, world, timed,
+                           steps=int(os.environ.get("PKB_BENCH_QL_STEPS", "6")))
 
 
 def main():
@@ -444,6 +563,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[2], 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-q-learning", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -11,7 +11,8 @@
  *   - no exceptions cross the ABI; no torch types; device pointers are plain void*
  *   - the handle owns the per-env device state; the caller owns action/output buffers
  *   - all launches are ordered on the cudaStream_t passed as `stream` (void*, may be NULL)
- *   - a handle is confined to one device and one host thread at a time
+ *   - a handle is confined to one device and one host thread at a time; its calls may move between streams (a call
+ *     on a new stream is ordered after everything the handle submitted to the previous one)
  *   - there is no CPU fallback: without a CUDA device every compute call fails
  *
  * Encodings (identical to the reference)
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PKB_ABI_VERSION 2
+#define PKB_ABI_VERSION 3
 #define PKB_MAX_PLAYERS 10
 #define PKB_NUM_MOVES 7
 
@@ -113,6 +114,14 @@ int pkb_destroy(pkb_env *h);
 int pkb_reset(pkb_env *h, const uint8_t *env_mask, void *stream);
 /* The `dealer` keyword of Game.reset(dealer=...), game.py:403: used by every later reset (and auto-reset). */
 int pkb_set_reset_dealer(pkb_env *h, int32_t dealer);
+/* Recomputes the valid-move mask cached in `meta` (bits 23-29) from the state planes.  pkb_step_random draws from the
+ * cached mask; call this after writing credits / pending_bets / minimum_raise_value / meta through pkb_state().
+ * (pkb_step and pkb_step_u8 always check the action against the planes as they are, game.py:648.) */
+int pkb_refresh_valid(pkb_env *h, void *stream);
+/* Consecutive step launches of one stream normally overlap: a launch starts while its predecessor drains, and tiles are
+ * handed over one by one (programmatic dependent launch; results are identical).  enabled = 0 restores plain stream
+ * order between step launches (measurement, debugging). */
+int pkb_set_pipelining(pkb_env *h, int32_t enabled);
 /* Game.step, game.py:621-700 on every env.  actions: device i32[N].  flags/valid: device u8[N] out
  * (valid = bit a set iff move a is valid for the NEW active player, game.py:339-383); either may be NULL. */
 int pkb_step(pkb_env *h, const int32_t *actions, uint8_t *flags, uint8_t *valid, void *stream);

@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_PLAYERS = 10
 NUM_MOVES = 7
 
@@ -74,6 +74,8 @@ SYMBOLS = {
     "pkb_destroy": (C.c_int, [_vp]),
     "pkb_reset": (C.c_int, [_vp, _vp, _vp]),
     "pkb_set_reset_dealer": (C.c_int, [_vp, _i32]),
+    "pkb_refresh_valid": (C.c_int, [_vp, _vp]),
+    "pkb_set_pipelining": (C.c_int, [_vp, _i32]),
     "pkb_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pkb_step_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pkb_step_random": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp]),
@@ -106,13 +108,17 @@ def lib():
     global _lib
     if _lib is None:
         path = os.environ.get("PKB_LIB") or _build.LIB  # PKB_LIB: load an experimental build instead
-        if not os.path.exists(path):
-            try:
+        if not os.environ.get("PKB_LIB"):
+            try:  # (re)build when the library is missing or older than its sources; a no-op when it is fresh
                 _build.build_native()
             except Exception as e:  # no silent fallback: the CUDA extension IS the product
-                raise ImportError(
-                    f"pokerl_b200: CUDA extension {path} is missing and could not be built ({e}). "
-                    "Run `python -m pokerl_b200._build` on a machine with nvcc.") from e
+                if not os.path.exists(path):
+                    raise ImportError(
+                        f"pokerl_b200: CUDA extension {path} is missing and could not be built ({e}). "
+                        "Run `python -m pokerl_b200._build` on a machine with nvcc.") from e
+                if _build.is_stale():
+                    import warnings
+                    warnings.warn(f"pokerl_b200: {path} is older than its sources and could not be rebuilt ({e})")
         L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol

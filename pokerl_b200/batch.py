@@ -153,18 +153,40 @@ class GameBatch:
         nat.check(nat.lib().pkb_set_reset_dealer(self._h.ptr, int(dealer)))
         self.config.dealer = int(dealer)
 
+    def refresh_valid(self):
+        """Recompute the cached valid-move masks after writing the state planes (credits, pending_bets, ...) directly."""
+        nat.check(nat.lib().pkb_refresh_valid(self._h.ptr, self._stream()))
+
+    def set_pipelining(self, enabled: bool):
+        """Whether consecutive step launches may overlap (default on; results are identical either way)."""
+        nat.check(nat.lib().pkb_set_pipelining(self._h.ptr, int(bool(enabled))))
+
     def reset(self, env_mask=None):
         """Game.reset() on every env, or on those where env_mask (uint8/bool [N]) is nonzero."""
         if env_mask is not None:
             env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
         nat.check(nat.lib().pkb_reset(self._h.ptr, nat.ptr(env_mask), self._stream()))
 
+    def _out(self, t, default, name):
+        """A caller-supplied output buffer goes to the kernel by raw pointer: it has to be what the kernel writes."""
+        if t is None:
+            return default
+        if not (isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and t.device == self.device and t.is_contiguous()
+                and t.numel() >= self.num_envs):
+            raise ValueError(f"{name} must be a contiguous uint8 tensor of at least {self.num_envs} elements on {self.device}")
+        return t
+
     def step(self, actions, flags=None, valid=None):
-        """Game.step(actions[i]) on env i.  actions: int32 [N] on this device, or uint8 [N] (one byte per move index,
-        255 = skip: a quarter of the bytes when the actions come from the host).  Returns (flags, valid)."""
-        flags = self.flags if flags is None else flags
-        valid = self.valid if valid is None else valid
-        if actions.dtype == torch.uint8 and actions.device == self.device and actions.is_contiguous():
+        """Game.step(actions[i]) on env i.  actions: int32 [N], or uint8 [N] (one byte per move index, 255 = skip: a
+        quarter of the bytes when the actions come from the host); tensors that live elsewhere or are not contiguous
+        are brought to this device in their own encoding first.  Returns (flags, valid)."""
+        flags, valid = self._out(flags, self.flags, "flags"), self._out(valid, self.valid, "valid")
+        actions = torch.as_tensor(actions)
+        if actions.numel() < self.num_envs:
+            raise ValueError(f"need {self.num_envs} actions, got {actions.numel()}")
+        if actions.dtype == torch.uint8:  # the byte encoding keeps its meaning (255 = skip) wherever the tensor lives
+            if actions.device != self.device or not actions.is_contiguous():
+                actions = actions.to(device=self.device).contiguous()
             nat.check(nat.lib().pkb_step_u8(self._h.ptr, nat.ptr(actions), nat.ptr(flags), nat.ptr(valid), self._stream()))
             return flags, valid
         if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
@@ -175,8 +197,7 @@ class GameBatch:
     def step_random(self, step_idx, weights=None, record_actions=False, flags=None, valid=None):
         """One step with the on-device random agent (uniform, or integer `weights` per move)."""
         w = None if weights is None else (C.c_uint32 * nat.NUM_MOVES)(*[int(x) for x in weights])
-        flags = self.flags if flags is None else flags
-        valid = self.valid if valid is None else valid
+        flags, valid = self._out(flags, self.flags, "flags"), self._out(valid, self.valid, "valid")
         out = self.actions_taken if record_actions else None
         nat.check(nat.lib().pkb_step_random(self._h.ptr, int(step_idx) & 0xFFFFFFFF, w, nat.ptr(out), nat.ptr(flags),
                                             nat.ptr(valid), self._stream()))

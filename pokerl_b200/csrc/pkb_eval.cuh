@@ -552,4 +552,35 @@ struct WinnerScan {
     }
 };
 
+// The same scan in closed form over P packed rankings held in registers (no loop-carried state, selects only): let m be
+// the best category present and K0 the kickers of the FIRST seat of that category (NONE: 0).  Seats of category m whose
+// kickers beat K0 replace the list, the LAST of them surviving; seats that equal K0 join whatever list exists when they
+// are met.  So: if some seat beats K0, the winners are the last such seat j plus the K0-equal seats after j; otherwise
+// all K0-equal seats.  Checked against WinnerScan on random and exhaustive small inputs (tests/test_host_logic.py).
+template <int P>
+PKB_HD uint32_t winners_closed(const uint32_t (&rk)[P])
+{
+    uint32_t m = rk[0] >> 20;
+#pragma unroll
+    for (int i = 1; i < P; ++i) m = (rk[i] >> 20) < m ? rk[i] >> 20 : m;
+    uint32_t k0 = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const bool first = !found && (rk[i] >> 20) == m;
+        k0 = first ? rk[i] & 0xfffffu : k0;
+        found |= first;
+    }
+    const uint32_t bar = m << 20 | k0;  // same category: packed values order like their kickers
+    uint32_t gt = 0, eq = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        gt |= (uint32_t)((rk[i] >> 20) == m && rk[i] > bar) << i;
+        eq |= (uint32_t)(rk[i] == bar) << i;
+    }
+    if (!gt) return eq;
+    const int j = topbit32(gt);
+    return 1u << j | (eq & ~((2u << j) - 1u));
+}
+
 }  // namespace pkb

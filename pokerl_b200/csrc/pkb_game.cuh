@@ -502,13 +502,26 @@ PKB_D void showdown_deal(V& v, size_t s, uint64_t seed, uint32_t env_id, uint32_
 #pragma unroll
         for (int p = 0; p < P; ++p) pd[p * ld + s] = 1ull << id[5 + 2 * p] | 1ull << id[6 + 2 * p];
     } else {
-        Dealer d(seed, env_id, episode, v.hand[s]);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) board |= 1ull << d.next();
+        // larger tables: one Philox block and its four draws per trip of a rolled loop (straight-line code inside, so the
+        // warp's lanes stay together: the sequential Dealer's out-of-line calls ran lane group by lane group)
+        constexpr int N = 5 + 2 * P, NB = (N + 3) / 4;
+        const uint32_t hand = v.hand[s];
+        uint64_t free_mask = (1ull << 52) - 1, pair = 0;
 #pragma unroll 1
-        for (int p = 0; p < P; ++p) {
-            const uint64_t a = 1ull << d.next();
-            pd[p * ld + s] = a | 1ull << d.next();
+        for (int b = 0; b < NB; ++b) {
+            const U4 blk = philox4x32_10_inl(U4{env_id, hand, episode, (uint32_t)b}, (uint32_t)seed, (uint32_t)(seed >> 32));
+            const uint32_t w[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * b + k;
+                if (i < N) {
+                    const uint64_t bit = 1ull << select_bit_inl(free_mask, mulhi32(w[k], (uint32_t)(52 - i)));
+                    free_mask &= ~bit;
+                    if (i < 5) board |= bit;  // draws 0..4: the board (game.py:278)
+                    else if (i & 1) pair = bit;                          // draw 5 + 2p: first hole card of seat p
+                    else pd[(size_t)((i - 6) >> 1) * ld + s] = pair | bit;  // draw 6 + 2p: second hole card of seat p
+                }
+            }
         }
     }
     reinterpret_cast<uint64_t*>(v.mr)[s] = board;
@@ -569,24 +582,17 @@ PKB_D void showdown_settle(V& v, size_t s, const Seats& x, int npw)
             const double bi = b[i] < 0.0 ? 0.0 : b[i];
             layer[i] = bi > max_bet ? max_bet : bi;
         }
-        WinnerScan ws;  // :512
-#pragma unroll
-        for (int i = 0; i < P; ++i) ws.feed(i, rk[i]);
+        const uint32_t winners = winners_closed<P>(rk);  // :512 compare_rankings
         const double S = np_sum<P>(layer);
-        const int nw = popc32(ws.winners);
-        if (nw == 1) {  // :515
+        const int nw = popc32(winners);
+        // :515 one winner takes S; :516 otherwise payoffs += (S * onehot) / sum(onehot).  A winner's share is S * 1.0 / nw;
+        // everybody else's is (S * 0.0) / nw, a signed zero, and adding a zero of either sign leaves a payoff as it is
+        // (payoffs start at +0.0 and a sum is -0.0 only if both terms are): ONE division per layer, not one per seat.
+        // Two seats can only tie two ways, and x / 2.0 == x * 0.5 exactly: no division sequence in the heads-up kernel.
+        const double share = nw == 1 ? S : P == 2 ? __dmul_rn(S, 0.5) : S / (double)nw;
 #pragma unroll
-            for (int i = 0; i < P; ++i)
-                if (ws.winners >> i & 1u) pay[i] += S;
-        } else {  // :516 (S * onehot) / sum(onehot)
-            const double k = (double)nw;
-#pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const double share = __dmul_rn(S, (ws.winners >> i & 1u) ? 1.0 : 0.0);
-                // two seats can only tie two ways: x / 2.0 == x * 0.5 exactly (no division sequence in the heads-up kernel)
-                pay[i] += P == 2 ? __dmul_rn(share, 0.5) : share / k;
-            }
-        }
+        for (int i = 0; i < P; ++i)
+            if (winners >> i & 1u) pay[i] += share;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
             if (i == p) rk[i] = PACKED_NONE;  // :522

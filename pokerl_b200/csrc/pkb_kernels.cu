@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/pokerl_b200.h"
@@ -446,7 +447,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 Seats x = load_seats<P>(v, s);
                 Meta m = unpack_meta(v.meta[s]);
                 const double hb = high_bet<P>(v, s), credit = v.cr[m.act * T + s];
-                const uint32_t vm = m.vm;  // = valid_mask_from(hb, credit, v.mr[s]), left in the meta word by the previous step / reset
+                // The sampler draws from the mask the previous step (or reset / pkb_refresh_valid) cached in the meta word; a
+                // caller's action is checked against get_valid_actions() of the planes as they are now (game.py:648), so
+                // that state the caller wrote through the zero-copy view is honoured.
+                const uint32_t vm = SAMPLE ? m.vm : valid_mask_from(hb, credit, v.mr[s]);
                 int action;
                 if (SAMPLE) {
                     const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
@@ -660,6 +664,18 @@ __global__ void reset_kernel(DevState d, GameConst gc, const uint8_t* mask)
     Seats x{0, 0, 0, 0};
     reset_env<P>(v, env, x, m, gc);
     store_seats<P>(v, env, x);
+    m.vm = valid_mask<P>(v, env, m.act);
+    d.meta[env] = pack_meta(m);
+}
+
+// recomputes the valid mask cached in the meta word (after the caller has written the state planes)
+template <int P>
+__global__ void refresh_valid_kernel(DevState d)
+{
+    const size_t env = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n) return;
+    const View<0> v = global_view(d);
+    Meta m = unpack_meta(d.meta[env]);
     m.vm = valid_mask<P>(v, env, m.act);
     d.meta[env] = pack_meta(m);
 }
@@ -961,6 +977,7 @@ struct pkb_env {
     cudaStream_t last_stream;
     bool has_last;
     cudaEvent_t order_event;
+    bool pipelined;  // step launches may overlap their predecessor's tail (programmatic dependent launch)
 };
 
 static thread_local std::string g_error;
@@ -1019,6 +1036,8 @@ template <class K>
 static cudaError_t resident_blocks(K kernel, int threads, size_t smem, int device, int* cache)
 {
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
     if (cache[device]) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1061,7 +1080,7 @@ static cudaError_t step_grid(int device, int sm_count, uint64_t n, unsigned* gri
 // serialization so that it may start while the previous step launch of the stream is still draining (tiles are handed
 // over one by one through their epoch words, see epoch_wait).
 template <int P, bool SAMPLE>
-static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_count)
+static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_count, bool pipelined)
 {
     using L = WarpTile<P>;
     unsigned grid = 0;
@@ -1076,9 +1095,8 @@ static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_c
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    static const bool no_pdl = getenv("PKB_NO_PDL") != nullptr;  // measurement switch: plain stream order between step launches
     cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.numAttrs = pipelined ? 1 : 0;  // pkb_set_pipelining(h, 0): plain stream order between step launches
     return cudaLaunchKernelEx(&cfg, step_warp_kernel<P, SAMPLE>, a);
 }
 
@@ -1218,6 +1236,7 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     }
     h->has_last = false;
     h->last_stream = nullptr;
+    h->pipelined = getenv("PKB_NO_PDL") == nullptr;
     e = cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaFree(h->arena);
@@ -1245,6 +1264,24 @@ int pkb_set_reset_dealer(pkb_env* h, int32_t dealer)
     h->cfg.dealer = dealer;
     h->gc.dealer = dealer;
     PKB_DISPATCH_P(h->cfg.num_players, fill_fresh_state<P>(h->gc));
+    return 0;
+}
+
+int pkb_set_pipelining(pkb_env* h, int32_t enabled)
+{
+    if (!h) return fail("pkb_set_pipelining: null handle");
+    h->pipelined = enabled != 0;
+    return 0;
+}
+
+int pkb_refresh_valid(pkb_env* h, void* stream)
+{
+    if (!h) return fail("pkb_refresh_valid: null handle");
+    PKB_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s));
+    PKB_DISPATCH_P(h->cfg.num_players, (refresh_valid_kernel<P><<<blocks_for(h->d.n, 256), 256, 0, s>>>(h->d)));
+    PKB_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -1283,8 +1320,8 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     PKB_CUDA(order_on_stream(h, s));
     cudaError_t e = cudaSuccess;
     PKB_DISPATCH_P(h->cfg.num_players,
-                   e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count)
-                              : launch_step<P, false>(a, s, h->cfg.device, h->sm_count));
+                   e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count, h->pipelined)
+                              : launch_step<P, false>(a, s, h->cfg.device, h->sm_count, h->pipelined));
     if (e != cudaSuccess) return fail("pkb_step: launch", e);
     return 0;
 }
@@ -1453,9 +1490,12 @@ int pkb_eval_cards(const uint8_t* cards, int32_t k, uint64_t n, uint32_t* out, v
 }
 
 // builds the evaluator's rank-set table on the current device the first time a batch evaluator runs there
+static std::mutex g_tables_mutex;  // the per-device table caches below are shared by every host thread
+
 static cudaError_t ensure_eval_table(cudaStream_t s)
 {
     static bool ready[64] = {false};
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -1463,6 +1503,7 @@ static cudaError_t ensure_eval_table(cudaStream_t s)
     if (!ready[dev]) {
         eval_table_init_kernel<<<EVAL_TABLE_SIZE / 256, 256, 0, s>>>();
         e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // built once: a first use from another stream must see all of it
         if (e == cudaSuccess) ready[dev] = true;
     }
     return e;
@@ -1474,6 +1515,7 @@ static cudaError_t ensure_eval_hash_tables(EvalHashTables* out)
 {
     static EvalHashTables tabs[64];
     static bool ready[64] = {false};
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -1540,6 +1582,7 @@ static cudaError_t ensure_binom()
 {
     static bool done = false;  // per process; constant memory is per device context
     static int done_device = -1;
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     if (done && done_device == dev) return cudaSuccess;

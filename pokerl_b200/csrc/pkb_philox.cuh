@@ -40,6 +40,22 @@ PKB_HD U4 philox4x32_10_inl(U4 c, uint32_t k0, uint32_t k1)
 PKB_HD_CALL U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) { return philox4x32_10_inl(c, k0, k1); }
 
 // position of the j-th (0-based) set bit of a 52-bit mask; j < popcount(f)
+PKB_HD uint32_t select_bit_inl(uint64_t f, uint32_t j)
+{
+    uint32_t w = (uint32_t)f, pos = 0;
+    uint32_t c = (uint32_t)popc32(w);
+    bool up = j >= c;
+    j -= up ? c : 0u; w = up ? (uint32_t)(f >> 32) : w; pos = up ? 32u : 0u;
+    c = (uint32_t)popc32(w & 0xffffu); up = j >= c;
+    j -= up ? c : 0u; w = up ? w >> 16 : w; pos += up ? 16u : 0u;
+    c = (uint32_t)popc32(w & 0xffu); up = j >= c;
+    j -= up ? c : 0u; w = up ? w >> 8 : w; pos += up ? 8u : 0u;
+    c = (uint32_t)popc32(w & 0xfu); up = j >= c;
+    j -= up ? c : 0u; w = up ? w >> 4 : w; pos += up ? 4u : 0u;
+    c = (uint32_t)popc32(w & 0x3u); up = j >= c;
+    j -= up ? c : 0u; w = up ? w >> 2 : w; pos += up ? 2u : 0u;
+    return pos + (j >= (w & 1u) ? 1u : 0u);
+}
 PKB_HD_CALL uint32_t select_bit(uint64_t f, uint32_t j)
 {
     uint32_t w = (uint32_t)f, pos = 0;
@@ -151,6 +167,7 @@ PKB_HD int pick_weighted(uint32_t word, uint32_t valid_mask, const uint32_t* wei
 // the 7-bit mask, found by halving (low 4 bits, then 2, then 1)
 PKB_HD int pick_uniform(uint32_t word, uint32_t valid_mask)
 {
+    valid_mask |= 1u;  // FOLD is always valid (game.py:367): an empty (never computed) mask folds instead of running off the end
     uint32_t t = mulhi32(word, (uint32_t)popc32(valid_mask)), w = valid_mask;
     int pick = 0;
     uint32_t c = (uint32_t)popc32(w & 0xfu);

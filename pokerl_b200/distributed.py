@@ -44,6 +44,8 @@ def init_from_env(backend: str = None, device_index: int = None):
 def reduce_stats(stats: Dict, device=None, group=None) -> Dict:
     """Sum a GameBatch.stats() dict over all ranks (identity without a process group)."""
     P = len(stats["payoff_sum"])
+    if device is None and dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())  # NCCL reduces device tensors only
     vec = torch.tensor([float(stats[k]) for k in STAT_KEYS] + [float(x) for x in stats["payoff_sum"]],
                        dtype=torch.float64, device=device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

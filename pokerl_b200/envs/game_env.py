@@ -83,9 +83,18 @@ class PokerGameEnv(PokerEnv):
         return torch.where(mask, actions, torch.full_like(actions, nat.ACTION_SKIP))
 
     def _step_masked(self, actions: torch.Tensor):
-        """One launch; returns (game_over, hand_over) bool tensors, False where the table was skipped."""
-        done, hand, _ = self.game.step(actions)
-        return done, hand
+        """One launch; returns (game_over, hand_over) bool tensors, False where the table was skipped.
+
+        A table that reaches a state in which the reference would spin forever (game.py:607) or assert (game.py:473) is
+        flagged PKB_F_POISONED by the kernel; here it counts as a finished game, so the caller's reset re-arms it."""
+        done, hand, _ = self.game.step(actions, check=False)
+        flags = self.game.batch.flags
+        if self.game.check_actions and bool(((flags & nat.F_INVALID) != 0).any().item()):
+            env = int(torch.nonzero(flags & nat.F_INVALID)[0].item())
+            raise ValueError('Env %d player %d invalid move: `%d`' % (env, int(self.game.batch.active_player[env].item()),
+                                                                      int(actions[env].item())))
+        dead = (flags & nat.F_POISONED) != 0
+        return done | dead, hand | dead
 
     def _reset_batched(self, env_mask=None) -> Game.StateView:
         b = self.game.batch

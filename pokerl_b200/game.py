@@ -151,6 +151,7 @@ class Game:
         self._step_count = 0
         # like the reference before reset(): all ACTIVE, zero money (game.py:253-264)
         self.batch.seat_masks.fill_((1 << self.num_players) - 1)  # the ACTIVE field of the seat-mask word
+        self.batch.refresh_valid()  # get_valid_actions of the all-zero table (game.py:339-383), for the device sampler
 
     @staticmethod
     def _credits_arg(sc):

@@ -21,12 +21,14 @@ ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--eval", action="store_true")
 args = ap.parse_args()
 
-g = GameBatch(args.envs, args.players, 100, 2, 1, seed=0, auto_reset=True)
+nine = args.players == 9  # BASELINE.json configs[3]: unequal stacks, all-in heavy action mix
+g = GameBatch(args.envs, args.players, [20 * (i + 1) for i in range(9)] if nine else 100, 2, 1, seed=1 if nine else 0, auto_reset=True)
+w = [10, 30, 30, 5, 5, 5, 45] if nine else None
 g.reset()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for t in range(args.steps):
     flush.zero_()
-    g.step_random(t)
+    g.step_random(t, w)
 if args.eval:
     masks = random_hands(0, 1 << 24)
     for _ in range(3):

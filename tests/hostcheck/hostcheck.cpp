@@ -7,6 +7,15 @@
 #include "pkb_eval.cuh"
 #include "pkb_philox.cuh"
 
+// the closed form of the winner scan used by the step kernels' side-pot loop: winner mask of n (2..10) packed rankings
+template <int P>
+static uint32_t closed(const uint32_t* packed)
+{
+    uint32_t rk[P];
+    for (int i = 0; i < P; ++i) rk[i] = packed[i];
+    return pkb::winners_closed<P>(rk);
+}
+
 extern "C" {
 
 uint32_t hc_eval_mask(uint64_t m) { return pkb::eval_mask52(m); }
@@ -125,6 +134,40 @@ int hc_deal_ids(uint64_t seed, uint32_t env, uint32_t episode, uint32_t hand, in
 int hc_sample(uint64_t seed, uint32_t env, uint32_t step, uint32_t valid, const uint32_t* w)
 {
     return pkb::sample_action(seed, env, step, valid, w);
+}
+
+uint32_t hc_winners_closed(const uint32_t* packed, int n)
+{
+    switch (n) {
+        case 2: return closed<2>(packed);
+        case 3: return closed<3>(packed);
+        case 4: return closed<4>(packed);
+        case 5: return closed<5>(packed);
+        case 6: return closed<6>(packed);
+        case 7: return closed<7>(packed);
+        case 8: return closed<8>(packed);
+        case 9: return closed<9>(packed);
+        case 10: return closed<10>(packed);
+    }
+    return 0xffffffffu;
+}
+uint32_t hc_winners_scan(const uint32_t* packed, int n)
+{
+    pkb::WinnerScan ws;
+    for (int i = 0; i < n; ++i) ws.feed(i, packed[i]);
+    return ws.winners;
+}
+// position of the j-th set bit: the branch-free form against the out-of-line one
+uint32_t hc_select_bit_mismatches(uint64_t seed, uint64_t count)
+{
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const uint64_t f = x & ((1ull << 52) - 1);
+        const int n = pkb::popc64(f);
+        for (int j = 0; j < n; ++j) bad += pkb::select_bit_inl(f, (uint32_t)j) != pkb::select_bit(f, (uint32_t)j);
+    }
+    return (uint32_t)bad;
 }
 
 int hc_compare(const uint32_t* packed, int n, uint8_t* onehot)

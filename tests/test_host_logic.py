@@ -229,3 +229,30 @@ def test_env_and_agent_api_mirror_reference():
     if not torch.cuda.is_available():
         with pytest.raises(nat.PkbError):
             PokerGameEnv(agents=[RandomAgent()] * 3, num_players=4)
+
+
+def test_closed_form_winner_scan_equals_sequential_scan(hc):
+    """winners_closed (the side-pot loop's compare_rankings, judger.py:133-158) == the sequential WinnerScan: every
+    assignment of a small alphabet of rankings (NONE included) to 2..5 seats, and random draws for 6..10 seats."""
+    import itertools
+    hc.hc_winners_closed.restype = C.c_uint32
+    hc.hc_winners_closed.argtypes = [C.c_void_p, C.c_int]
+    hc.hc_winners_scan.restype = C.c_uint32
+    hc.hc_winners_scan.argtypes = [C.c_void_p, C.c_int]
+    alphabet = [10 << 20, 9 << 20 | 5, 9 << 20 | 7, 9 << 20 | 9, 8 << 20 | 3, 8 << 20 | 7, 1 << 20 | 13]
+    for n in range(2, 6):
+        for combo in itertools.product(alphabet, repeat=n):
+            a = np.array(combo, dtype=np.uint32)
+            assert hc.hc_winners_closed(a.ctypes.data, n) == hc.hc_winners_scan(a.ctypes.data, n), combo
+    rng = np.random.default_rng(5)
+    for n in range(6, 11):
+        for _ in range(20000):
+            a = (rng.integers(7, 11, n).astype(np.uint32) << 20) | rng.integers(0, 4, n).astype(np.uint32)
+            a[a >> 20 == 10] = 10 << 20
+            assert hc.hc_winners_closed(a.ctypes.data, n) == hc.hc_winners_scan(a.ctypes.data, n), a
+
+
+def test_branch_free_select_bit(hc):
+    hc.hc_select_bit_mismatches.restype = C.c_uint32
+    hc.hc_select_bit_mismatches.argtypes = [C.c_uint64, C.c_uint64]
+    assert hc.hc_select_bit_mismatches(3, 20000) == 0
