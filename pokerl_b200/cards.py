@@ -38,6 +38,15 @@ class Card:
     def from_id(cls, card_id: int) -> "Card":
         return cls(((card_id // 13) << 4) | (card_id % 13))
 
+    # pickled like the reference's plain-attribute class (state = {'value': v}), so either side can load the other's cards
+    def __getstate__(self):
+        return {"value": self.value}
+
+    def __setstate__(self, state):
+        if isinstance(state, tuple):  # (dict or None, slot dict)
+            state = {**(state[0] or {}), **(state[1] or {})}
+        self.value = int(state["value"])
+
     def __eq__(self, other):
         return isinstance(other, Card) and other.value == self.value
 

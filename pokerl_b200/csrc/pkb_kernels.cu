@@ -60,7 +60,7 @@ struct StepArgs {
     uint32_t use_weights;
     uint32_t weights[NUM_MOVES];
     uint32_t num_tiles;
-    uint32_t strict;  // tile hand-over between launches with a release store (see epoch_publish)
+    uint32_t wait_prev;  // the launch before this one on the stream is not a step launch of this handle: wait for it
 };
 
 #ifndef PKB_STRIDE_ALIGN
@@ -155,20 +155,17 @@ PKB_D void epoch_wait(const uint32_t* word, uint32_t want)
         if (polls > (1u << 22)) __trap();
     }
 }
-// What the flag store must come after: (1) the tile's rows, written by this thread's TMA stores -- `wait_group 0` returns
-// when they have been performed (they are in L2, the GPU's point of coherence), and the proxy fence orders that before
-// the generic-proxy flag store; (2) the warp's plain stores to the caller's output arrays and the payoff plane, which the
-// next launch never reads but may overwrite.  A release store covers both formally, at the price of a GPU-scope fence
-// per tile (it waits for every store the SM has in flight: measured 1.8 us of a 38 us step).  The default therefore
-// stores the flag relaxed: (1) holds by completion, and for (2) the next writer of the same address is a warp of the
-// next launch that first has to see this flag, load the tile and run its passes -- ten microseconds behind stores that
-// are performed in one.  `strict` (PKB_STRICT_HANDOVER=1) selects the release store.
-PKB_D void epoch_publish(uint32_t* word, uint32_t value, bool strict)
+// The flag store must come after (1) the tile's rows, written by this thread's TMA stores, and (2) the warp's plain
+// stores to the caller's output arrays and the payoff plane, which the next launch may overwrite.  `wait_group 0` alone
+// is NOT enough for (1): it returns when the writes are performed with respect to this thread, and a consumer on
+// another SM that sees a relaxed flag store a moment later can still load the old rows (measured: a 2^18-env batch,
+// whose launches overlap three deep, diverges from the oracle within 48 steps; tests/test_gpu_round2.py).  So the flag
+// is a release store at GPU scope (MEMBAR.ALL.GPU in SASS, about 1.5 us of a 38 us step).
+PKB_D void epoch_publish(uint32_t* word, uint32_t value)
 {
     bulk_wait_all();
     fence_async_global();
-    if (strict) st_release_u32(word, value);
-    else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(word), "r"(value) : "memory");
+    st_release_u32(word, value);
 }
 
 template <class L>
@@ -352,6 +349,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     __syncthreads();
     const uint32_t launch = s_launch;
     pdl_launch_dependents();  // the next step launch may start filling the SMs this one's finished blocks leave
+    // Launched with programmatic stream serialization, this grid may be running before its predecessor has completed.
+    // After another step launch of this handle that is the point (tiles are handed over one by one, see epoch_wait);
+    // after anything else -- a reset, a kernel of the caller's that wrote the state planes -- wait for it properly.
+    if (a.wait_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     Tally<P> tl;
 #pragma unroll
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         }
         // The previous tile's store was issued just before this tile's load: waiting for it to be performed and releasing
         // its epoch (a GPU-scope fence) costs about what the load takes, and the warp has nothing else to do until then.
-        if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u, a.strict != 0);
+        if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
         mbar_wait(bar, it & 1u);
 #ifdef PKB_TIMING
         wt_lw[it < 2 ? it : 2] += (unsigned long long)(clock64() - wt_last);
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         wt_acc[5] += 1;
 #endif
     }
-    if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u, a.strict != 0);
+    if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
 #ifdef PKB_TIMING
     {
         const uint32_t gw = blockIdx.x * L::WARPS + warp;
@@ -977,7 +978,8 @@ struct pkb_env {
     cudaStream_t last_stream;
     bool has_last;
     cudaEvent_t order_event;
-    bool pipelined;  // step launches may overlap their predecessor's tail (programmatic dependent launch)
+    bool pipelined;      // step launches may overlap their predecessor's tail (programmatic dependent launch)
+    bool last_was_step;  // the handle's previous launch was a step launch (on last_stream)
 };
 
 static thread_local std::string g_error;
@@ -1013,7 +1015,7 @@ static int fail(const char* what, cudaError_t e = cudaSuccess)
     }
 
 // orders the handle's next launch (on stream s) after its previous ones when the caller has switched streams
-static cudaError_t order_on_stream(pkb_env* h, cudaStream_t s)
+static cudaError_t order_on_stream(pkb_env* h, cudaStream_t s, bool step_launch = false)
 {
     cudaError_t e = cudaSuccess;
     if (h->has_last && h->last_stream != s) {
@@ -1024,6 +1026,7 @@ static cudaError_t order_on_stream(pkb_env* h, cudaStream_t s)
             e = cudaDeviceSynchronize();
         }
     }
+    h->last_was_step = step_launch && h->last_was_step && h->has_last && h->last_stream == s;
     h->last_stream = s;
     h->has_last = true;
     return e;
@@ -1237,6 +1240,7 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     h->has_last = false;
     h->last_stream = nullptr;
     h->pipelined = getenv("PKB_NO_PDL") == nullptr;
+    h->last_was_step = false;
     e = cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaFree(h->arena);
@@ -1313,16 +1317,21 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.valid = valid;
     a.step_idx = step_idx;
     a.use_weights = weights ? 1u : 0u;
-    static const bool strict = getenv("PKB_STRICT_HANDOVER") != nullptr && getenv("PKB_STRICT_HANDOVER")[0] == '1';
-    a.strict = strict ? 1u : 0u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    PKB_CUDA(order_on_stream(h, s));
+    PKB_CUDA(order_on_stream(h, s, true));
+    // Only the fused random-agent step is launched ahead of its predecessor's completion: all it reads is the handle's
+    // own state.  A step with the caller's actions reads a buffer some other kernel or copy of the stream has just
+    // produced, so it keeps plain stream order.  (Other work the caller puts on the stream BETWEEN two pkb_step_random
+    // calls must not write the handle's state; pkb_refresh_valid / pkb_reset between them are fine.)
+    const bool ahead = sample && h->pipelined;
+    a.wait_prev = h->last_was_step ? 0u : 1u;
     cudaError_t e = cudaSuccess;
     PKB_DISPATCH_P(h->cfg.num_players,
-                   e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count, h->pipelined)
-                              : launch_step<P, false>(a, s, h->cfg.device, h->sm_count, h->pipelined));
+                   e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count, ahead)
+                              : launch_step<P, false>(a, s, h->cfg.device, h->sm_count, ahead));
     if (e != cudaSuccess) return fail("pkb_step: launch", e);
+    h->last_was_step = true;
     return 0;
 }
 

@@ -27,6 +27,26 @@ from .cards import Card
 from .enums import PlayerState, PokerMoves
 
 
+def np_sum_rows(t: torch.Tensor) -> torch.Tensor:
+    """Row sums of a [N, P] float64 tensor in numpy's add.reduce order (what `np.sum(self.bets)` does, game.py:283):
+    fewer than eight terms left to right; from eight on, eight running lanes combined pairwise, then the tail."""
+    P = t.shape[1]
+    if P < 8:
+        r = torch.zeros_like(t[:, 0])
+        for p in range(P):
+            r = r + t[:, p]
+        return r
+    lanes = [t[:, j].clone() for j in range(8)]
+    full = P - P % 8
+    for k in range(8, full, 8):
+        for j in range(8):
+            lanes[j] = lanes[j] + t[:, k + j]
+    r = ((lanes[0] + lanes[1]) + (lanes[2] + lanes[3])) + ((lanes[4] + lanes[5]) + (lanes[6] + lanes[7]))
+    for p in range(full, P):
+        r = r + t[:, p]
+    return r
+
+
 class Game:
     """A Texas Hold'em game (scalar mode) or N of them in lockstep (batched mode)."""
 
@@ -88,7 +108,7 @@ class Game:
 
         @property
         def pot(self):
-            return self.bets.sum(dim=1) if self._batched else np.sum(self.bets)
+            return np_sum_rows(self.bets) if self._batched else np.sum(self.bets)
 
         @property
         def high_bet(self):
@@ -201,7 +221,7 @@ class Game:
 
     @property
     def pot(self):
-        return self.bets.sum(dim=1) if self.batched else np.sum(self.bets)
+        return np_sum_rows(self.bets) if self.batched else np.sum(self.bets)
 
     @property
     def high_bet(self):
