@@ -377,25 +377,27 @@ def run_ours(args, rank, local_rank, world):
     resident_ms = timed(one_batch) / KF
 
     # ---- end to end through the public API with HOST buffers.  Every step: H2D copy of that step's actions from
-    # pinned host memory, GameBatch.step, D2H copy of its flags and valid masks.  Independent batches take turns, each
-    # on its own stream, so one batch's copies overlap another batch's step (a caller that keeps several env batches
-    # in flight does exactly this; within a batch, copy-in -> step -> copy-out is a serial chain, so E2E_BATCHES of
-    # them are in flight); the actions are a recording of the device-side random agents, so every one of them is
-    # valid for the state it meets.
+    # pinned host memory (two moves per byte), GameBatch.step_packed, D2H copy of its result byte per env (done flags +
+    # valid mask) to pinned host memory.  Within a batch, copy-in -> step -> copy-out is a serial chain, so E2E_BATCHES
+    # independent batches are in flight, each on its own stream; each batch's chain of R steps is captured once in a CUDA
+    # graph (the copies read a different row of the pinned action recording every step) and replayed, which takes the
+    # per-step Python / ctypes issue cost out of the timed region.  The actions are a recording of the device-side
+    # random agents, so every one of them is valid for the state it meets.
     main = torch.cuda.current_stream(dev)
     R = max(1, min(K, 126) // E2E_BATCHES)  # rounds; E = R * E2E_BATCHES steps
     E = R * E2E_BATCHES
+    half = (N + 1) // 2
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(E2E_BATCHES)]
     host_actions, runs = [], []
     for j in range(E2E_BATCHES):
         rec = make_batch(j)
         rec.reset()
-        ha = torch.empty((R, N), dtype=torch.uint8).pin_memory()  # one byte per action (pkb_step_u8)
+        ha = torch.empty((R, half), dtype=torch.uint8).pin_memory()  # half a byte per action (pkb_step_packed)
         for r in range(PREROLL):
             rec.step_random(r)
         for r in range(R):
             rec.step_random(PREROLL + r, record_actions=True)
-            ha[r].copy_(rec.actions_taken.to(torch.uint8))
+            ha[r].copy_(GameBatch.pack_actions(rec.actions_taken))
         torch.cuda.synchronize()
         del rec
         host_actions.append(ha)
@@ -404,24 +406,38 @@ def run_ours(args, rank, local_rank, world):
         for r in range(PREROLL):
             run.step_random(r)
         runs.append(run)
-    dev_actions = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(E2E_BATCHES)]
-    host_out = [torch.empty((2, N), dtype=torch.uint8).pin_memory() for _ in range(E2E_BATCHES)]  # flags, valid
+    dev_actions = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(E2E_BATCHES)]
+    dev_out = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(E2E_BATCHES)]
+    host_out = [torch.empty((R, N), dtype=torch.uint8).pin_memory() for _ in range(E2E_BATCHES)]  # every step's result byte
+    for j in range(E2E_BATCHES):  # move every handle to its own stream before the capture (a handle that changes
+        with torch.cuda.stream(e2e_streams[j]):  # streams orders itself with an event, which a capture cannot contain)
+            e2e_streams[j].wait_stream(main)
+            runs[j].refresh_valid()
+    torch.cuda.synchronize()
+    graphs = []
+    for j in range(E2E_BATCHES):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=e2e_streams[j]):
+            for r in range(R):
+                dev_actions[j].copy_(host_actions[j][r], non_blocking=True)
+                runs[j].step_packed(dev_actions[j], out=dev_out[j])
+                host_out[j][r].copy_(dev_out[j], non_blocking=True)
+        graphs.append(gr)
     barrier()
     t0 = time.perf_counter()
     for st in e2e_streams:
         st.wait_stream(main)
-    for r in range(R):
-        for j in range(E2E_BATCHES):
-            with torch.cuda.stream(e2e_streams[j]):
-                dev_actions[j].copy_(host_actions[j][r], non_blocking=True)
-                runs[j].step(dev_actions[j])
-                host_out[j].copy_(runs[j].outputs, non_blocking=True)
+    for j in range(E2E_BATCHES):
+        with torch.cuda.stream(e2e_streams[j]):
+            graphs[j].replay()
     for st in e2e_streams:
         st.synchronize()
     e2e_s = time.perf_counter() - t0
+    # every byte that came back is a step result: R * N env-steps per batch, none rejected
+    done_seen = sum(int((ho & 1).sum().item()) for ho in host_out)
     rejected = sum(run.stats()["invalid"] for run in runs)
     assert rejected == 0, f"e2e replay produced {rejected} rejected actions"
-    del runs, batches, g
+    del runs, batches, g, graphs
 
     # ---- BASELINE.json configs[3]: nine players, unequal stacks, all-in heavy mix, 2^22 GLOBAL envs sharded over the ranks
     from pokerl_b200 import distributed as D
@@ -503,10 +519,12 @@ def run_ours(args, rank, local_rank, world):
                      "unpipelined_frac": bytes_per_launch / (unpipelined_ms / 1e3) / 1e9 / peak,
                      "unpipelined_note": "pkb_set_pipelining(0): every launch alone on the GPU, its tail not overlapped",
                      "peak_source": peak_src},
-        "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": N,
-                "d2h_bytes_per_step": 2 * N, "steps": E,
-                "path": "per step: one byte per action H2D from pinned host -> GameBatch.step -> pkb_step_u8 -> flags+valid D2H (one copy) to pinned host; "
-                        f"{E2E_BATCHES} resident batches take turns on {E2E_BATCHES} streams, host synchronises at the end"},
+        "e2e": {"value": N * world * E / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": (N + 1) // 2,
+                "d2h_bytes_per_step": N, "steps": E, "games_over_seen_on_host": done_seen,
+                "path": "per step: half a byte per action H2D from pinned host -> GameBatch.step_packed -> pkb_step_packed -> one result "
+                        "byte per env (done flags + valid mask) D2H to pinned host; "
+                        f"{E2E_BATCHES} independent batches in flight on {E2E_BATCHES} streams, each batch's chain of {R} steps "
+                        "captured in one CUDA graph and replayed inside the timed region; host synchronises at the end"},
         "gpu_launches": K,  # one persistent step_warp_kernel launch per step
         "clocks": clock_info,
         "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",

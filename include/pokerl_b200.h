@@ -130,6 +130,15 @@ int pkb_step(pkb_env *h, const int32_t *actions, uint8_t *flags, uint8_t *valid,
  * whose actions come from the host every step. */
 #define PKB_ACTION_SKIP_U8 255
 int pkb_step_u8(pkb_env *h, const uint8_t *actions, uint8_t *flags, uint8_t *valid, void *stream);
+/* The same step in its most compact host-facing form, for callers that ship actions up and results down every step:
+ * actions_u4 = device u8[(N+1)/2], two move indices per byte (env 2i in the low nibble, env 2i+1 in the high one;
+ * PKB_ACTION_SKIP_U4 leaves the env alone, 7..14 are rejected); packed_out = device u8[N], one byte per env:
+ * bits 0-2 = PKB_F_GAME_OVER | PKB_F_HAND_OVER | PKB_F_ROUND_OVER, bits 3-7 = valid bits of moves 1..5 (CHECK, CALL,
+ * RAISE_TEN, RAISE_QUARTER, RAISE_HALF) for the NEW active player -- FOLD and ALL_IN are always valid (game.py:367).
+ * Rejected / poisoned steps do not fit the byte: they are counted (pkb_stats: invalid, poisoned) and leave bits 0-2
+ * zero.  1.5 bytes per env-step cross PCIe instead of 3 (pkb_step_u8) or 6 (pkb_step). */
+#define PKB_ACTION_SKIP_U4 15
+int pkb_step_packed(pkb_env *h, const uint8_t *actions_u4, uint8_t *packed_out, void *stream);
 /* Same, with the action drawn on device: weighted choice over the valid mask from
  * Philox(seed, env_id, step_idx) (RandomAgent, agents/random.py:16-17 when weights == NULL).
  * weights: host u32[7] or NULL.  actions_out: device i32[N] or NULL (the actions taken, for replay). */

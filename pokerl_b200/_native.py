@@ -78,6 +78,7 @@ SYMBOLS = {
     "pkb_set_pipelining": (C.c_int, [_vp, _i32]),
     "pkb_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pkb_step_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pkb_step_packed": (C.c_int, [_vp, _vp, _vp, _vp]),
     "pkb_step_random": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "pkb_sample_actions": (C.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "pkb_valid_actions": (C.c_int, [_vp, _i32, _vp, _vp]),

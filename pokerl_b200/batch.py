@@ -84,6 +84,7 @@ class GameBatch:
             self.outputs = torch.zeros((2, self.num_envs), dtype=torch.uint8, device=self.device)
             self.flags, self.valid = self.outputs[0], self.outputs[1]
             self.actions_taken = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            self._packed = None
 
     # ---- zero-copy state ---------------------------------------------------------------------
     def _wrap_state(self):
@@ -193,6 +194,34 @@ class GameBatch:
             actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
         nat.check(nat.lib().pkb_step(self._h.ptr, nat.ptr(actions), nat.ptr(flags), nat.ptr(valid), self._stream()))
         return flags, valid
+
+    def step_packed(self, actions_u4, out=None):
+        """Game.step in the compact encoding of pkb_step_packed: `actions_u4` uint8 [(N+1)//2] on this device, two moves per
+        byte (see pack_actions); returns uint8 [N]: flags bits 0-2 | valid bits of moves 1..5 << 3 (see unpack_outputs)."""
+        if out is None:
+            if self._packed is None:
+                self._packed = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            out = self._packed
+        out = self._out(out, None, "out")
+        if not (isinstance(actions_u4, torch.Tensor) and actions_u4.dtype == torch.uint8 and actions_u4.device == self.device
+                and actions_u4.is_contiguous() and actions_u4.numel() >= (self.num_envs + 1) // 2):
+            raise ValueError(f"actions_u4 must be a contiguous uint8 tensor of {(self.num_envs + 1) // 2} bytes on {self.device}")
+        nat.check(nat.lib().pkb_step_packed(self._h.ptr, nat.ptr(actions_u4), nat.ptr(out), self._stream()))
+        return out
+
+    @staticmethod
+    def pack_actions(actions):
+        """int moves [N] (-2**31 or 15 = skip) -> uint8 [(N+1)//2], two per byte, env 2i in the low nibble."""
+        a = torch.as_tensor(actions)
+        a = torch.where((a < 0) | (a > 14), torch.full_like(a, 15), a).to(torch.uint8)
+        if a.numel() % 2:
+            a = torch.cat([a, torch.full((1,), 15, dtype=torch.uint8, device=a.device)])
+        return (a[0::2] | (a[1::2] << 4)).contiguous()
+
+    @staticmethod
+    def unpack_outputs(packed):
+        """packed uint8 [N] -> (flags uint8 [N] with bits 0-2, valid uint8 [N] seven-bit masks)."""
+        return packed & 7, ((packed >> 3) << 1) | 0x41
 
     def step_random(self, step_idx, weights=None, record_actions=False, flags=None, valid=None):
         """One step with the on-device random agent (uniform, or integer `weights` per move)."""

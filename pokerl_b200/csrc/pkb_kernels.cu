@@ -53,6 +53,8 @@ struct StepArgs {
     GameConst gc;
     const int32_t* actions;
     const uint8_t* actions_u8;  // compact form of `actions` (255 = skip); used when `actions` is null
+    const uint8_t* actions_u4;  // two moves per byte (env 2i in the low nibble; 15 = skip); used when both others are null
+    uint8_t* packed;            // or null: one output byte per env, flags bits 0-2 | valid bits of moves 1..5 << 3
     int32_t* actions_out;
     uint8_t* flags;
     uint8_t* valid;
@@ -400,8 +402,12 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     if (a.actions) {
                         const int32_t x = a.actions[env];
                         b = x == ACTION_SKIP ? 255u : (x < 0 || x > 253) ? 254u : (uint32_t)x;
-                    } else
+                    } else if (a.actions_u8) {
                         b = a.actions_u8[env];
+                    } else {
+                        const uint32_t nib = (uint32_t)a.actions_u4[env >> 1] >> (4u * (uint32_t)(env & 1u)) & 15u;
+                        b = nib == 15u ? 255u : nib;  // 7..14 are out of range like any other number
+                    }
                 }
                 act_row[lane + 32 * k] = (uint8_t)b;
             }
@@ -601,6 +607,10 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         __syncwarp();
         if (SAMPLE && a.actions_out)
             for (int s = lane; s < T && base + s < d.n; s += 32) a.actions_out[base + s] = act_row[s];
+        if (a.packed) {  // the compact output: FOLD and ALL_IN are always valid (game.py:367), so five mask bits say it all
+            for (int s = lane; s < T && base + s < d.n; s += 32)
+                a.packed[base + s] = (uint8_t)((out_f[s] & 7u) | (out_v[s] >> 1 & 31u) << 3);
+        }
         if (out_words && base + T <= d.n) {  // the two output rows: one 32-bit store per lane and 32 slots
 #pragma unroll
             for (int w = lane; w < T / 4; w += 32) {
@@ -1301,10 +1311,11 @@ int pkb_reset(pkb_env* h, const uint8_t* env_mask, void* stream)
 }
 
 static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_t* weights, const int32_t* actions,
-                       const uint8_t* actions_u8, int32_t* actions_out, uint8_t* flags, uint8_t* valid, void* stream)
+                       const uint8_t* actions_u8, int32_t* actions_out, uint8_t* flags, uint8_t* valid, void* stream,
+                       const uint8_t* actions_u4 = nullptr, uint8_t* packed = nullptr)
 {
     if (!h) return fail("pkb_step: null handle");
-    if (!sample && !actions && !actions_u8) return fail("pkb_step: null actions");
+    if (!sample && !actions && !actions_u8 && !actions_u4) return fail("pkb_step: null actions");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
     StepArgs a;
     a.maps = h->maps;
@@ -1312,6 +1323,8 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.gc = h->gc;
     a.actions = actions;
     a.actions_u8 = actions_u8;
+    a.actions_u4 = actions_u4;
+    a.packed = packed;
     a.actions_out = actions_out;
     a.flags = flags;
     a.valid = valid;
@@ -1343,6 +1356,12 @@ int pkb_step(pkb_env* h, const int32_t* actions, uint8_t* flags, uint8_t* valid,
 int pkb_step_u8(pkb_env* h, const uint8_t* actions, uint8_t* flags, uint8_t* valid, void* stream)
 {
     return step_common(h, false, 0, nullptr, nullptr, actions, nullptr, flags, valid, stream);
+}
+
+int pkb_step_packed(pkb_env* h, const uint8_t* actions_u4, uint8_t* packed_out, void* stream)
+{
+    if (!actions_u4 || !packed_out) return fail("pkb_step_packed: null argument");
+    return step_common(h, false, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream, actions_u4, packed_out);
 }
 
 int pkb_step_random(pkb_env* h, uint32_t step_idx, const uint32_t* weights, int32_t* actions_out, uint8_t* flags,

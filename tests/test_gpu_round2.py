@@ -215,3 +215,37 @@ def test_output_buffers_are_checked(torch_cuda):
         g.step(a[:10])
     f1, _ = g.step(torch.full((100,), 255, dtype=torch.uint8))  # host uint8 keeps its encoding: 255 = skip
     assert bool((f1 == 32).all().item())
+
+
+def test_packed_step_equals_plain_step(torch_cuda, ora):
+    """pkb_step_packed (two moves per byte in, one byte per env out) == pkb_step on the same actions: outputs, state,
+    skips; an odd env count exercises the last half-filled byte."""
+    torch = torch_cuda
+    from pokerl_b200 import GameBatch
+    from pokerl_b200 import _native as nat
+    N, P, T = 20001, 3, 40
+    a_batch = GameBatch(N, P, 60, 2, 1, seed=8, auto_reset=True)
+    b_batch = GameBatch(N, P, 60, 2, 1, seed=8, auto_reset=True)
+    a_batch.reset(); b_batch.reset()
+    gen = torch.Generator(device=a_batch.device).manual_seed(1)
+    for t in range(T):
+        acts = a_batch.sample_actions(t).clone()
+        skip = torch.rand(N, device=acts.device, generator=gen) < 0.1
+        acts = torch.where(skip, torch.full_like(acts, nat.ACTION_SKIP), acts)
+        flags, valid = a_batch.step(acts)
+        packed = b_batch.step_packed(GameBatch.pack_actions(acts))
+        f2, v2 = GameBatch.unpack_outputs(packed)
+        assert torch.equal(f2, flags & 7), t
+        assert torch.equal(v2, valid), t
+        assert bool(((flags & nat.F_SKIPPED) != 0).eq(skip).all().item()), t
+    ea, eb = a_batch.export(), b_batch.export()
+    for k in F64_KEYS:
+        assert np.array_equal(np.ascontiguousarray(ea[k]).view(np.uint64), np.ascontiguousarray(eb[k]).view(np.uint64)), k
+    for k in INT_KEYS:
+        assert np.array_equal(ea[k], eb[k]), k
+    sa, sb = a_batch.stats(), b_batch.stats()
+    assert {k: v for k, v in sa.items() if k != "payoff_sum"} == {k: v for k, v in sb.items() if k != "payoff_sum"}
+    assert np.allclose(sa["payoff_sum"], sb["payoff_sum"], rtol=1e-9)  # float atomics: the order of the adds is not fixed
+    bad = GameBatch.pack_actions(torch.full((N,), 9, dtype=torch.int32, device=a_batch.device))  # 7..14: rejected
+    b_batch.step_packed(bad)
+    assert b_batch.stats()["invalid"] == N
