@@ -5,20 +5,20 @@
     python bench.py --impl reference [--gpus N] ...                # the unmodified reference on the host cores
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # N > 1: one rank per GPU
 
-Headline workload (BASELINE.json configs[2]): heads-up NLHE, 2^20 lockstep envs PER GPU, start_credits 100, blinds
-2/1, uniform random agents drawn on device from Philox(seed 0, global env id, step), auto-reset on game over.  One
-bench "step" = one Game.step on every env of one batch = ONE launch of the fused sample+step kernel
-(pkb::step_warp_kernel).  Envs shard by contiguous global-id slices; there is no data-path collective (weak scaling);
-one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
+Headline workload (BASELINE.json configs[2]): heads-up NLHE in lockstep batches of 2^20 envs, start_credits 100,
+blinds 2/1, uniform random agents drawn on device from Philox(seed 0, global env id, step), auto-reset on game over.
+One 2^20-env batch (92 MB of state) would fit the 126 MB L2, so each GPU holds THREE such batches ("inputs larger than
+L2") and one bench "step" = one Game.step on every resident env = THREE launches of the fused sample+step kernel
+(pkb::step_warp_kernel), one per batch, on one stream: every launch streams its batch from HBM and back, because the
+other two batches pushed it out of L2.  Envs shard by contiguous global-id slices; there is no data-path collective
+(weak scaling); one NCCL all-reduce of the payoff/statistics vector runs after the timed region.
 
 Timing: every batch is first rolled PREROLL steps forward (untimed set-up) so that the timed steps meet the
 steady-state mix of streets, hand ends and showdowns instead of 2^20 tables that were all dealt at the same moment;
 then W untimed warm-up steps, then K timed steps inside a barrier + synchronize bracket, timed with one CUDA event
-pair; the reported time is the max over ranks.  One 2^20-env batch (92 MB of state) would fit the 126 MB L2, so each
-GPU holds THREE such batches ("inputs larger than L2") and steps them round-robin on ONE stream: every step is one
-pass of the hot path over one batch whose state was pushed out of L2 by the steps of the other two, i.e. it streams
-from HBM and back.  Consecutive step launches of a stream overlap inside the library (programmatic dependent launch
-with a per-tile hand-over): `ms_per_step` is the launch INTERVAL of that pipeline, and
+pair; the reported time is the max over ranks.  Consecutive step launches of a stream overlap inside the library
+(programmatic dependent launch with a per-tile hand-over): `roofline.avg_launch_us` is the launch
+INTERVAL of that pipeline (timed region / launches, ramp-up and drain included), and
 `roofline.unpipelined_launch_us` is the duration of one launch with nothing else on the GPU.
 
 The same JSON line carries BASELINE.json configs[3] (`nine_player`: 2^22 global envs sharded over the ranks, unequal
@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(num_players=2, start_credits=100, big_blind=2, small_blind=1, seed=0)
 ENVS_PER_GPU = 1 << 20
 RESIDENT_BATCHES = 3  # 3 x 92 MB of env state per GPU: larger than the 126 MB L2
+REPEATS = 5           # the K-step timed region is repeated this often; the median is reported
 PREROLL = 64          # untimed steps every batch is rolled forward before anything is measured (steady-state hand mix)
 E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "6"))  # env batches the end-to-end leg keeps in flight
 L2_FLUSH_BYTES = 256 << 20
@@ -260,11 +261,11 @@ def run_reference(args, rank, world):
     value = base["value"]
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ENVS_PER_GPU / value * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ENVS_PER_GPU * RESIDENT_BATCHES / value * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(ENVS_PER_GPU, world, note="CPU arm: each timed sample is a bounded run of the same "
                                   "workload (tables stepped for a fixed time per process); ms_per_step = the time one "
-                                  "2^20-env step would take at the measured rate"),
+                                  "step over all resident envs would take at the measured rate"),
         "cpu_baseline": base, "cpu_baseline_port": port,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -274,16 +275,17 @@ def run_reference(args, rank, world):
 
 def workload_config(envs_per_gpu, world, note=None):
     cfg = {"workload": "heads-up NLHE, random agents (BASELINE.json configs[2])", "num_players": WORKLOAD["num_players"],
-           "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world, "start_credits": WORKLOAD["start_credits"],
+           "lockstep_batch_envs": envs_per_gpu, "envs_per_gpu": envs_per_gpu * RESIDENT_BATCHES,
+           "global_envs": envs_per_gpu * RESIDENT_BATCHES * world, "start_credits": WORKLOAD["start_credits"],
            "blinds": [WORKLOAD["big_blind"], WORKLOAD["small_blind"]], "agents": "uniform random over valid actions, on device",
            "auto_reset": True, "seed": WORKLOAD["seed"], "sharding": f"env-sliced x{world}, no data-path collective",
            "resident_batches_per_gpu": RESIDENT_BATCHES,
            "preroll_steps": PREROLL,
            "preroll": f"every batch is stepped {PREROLL} times before warm-up (untimed set-up): steady-state mix of streets, "
                       "hand ends and showdowns",
+           "step": f"one Game.step on every resident env: {RESIDENT_BATCHES} launches (one per {envs_per_gpu}-env batch) on one stream",
            "l2": f"inputs larger than L2: {RESIDENT_BATCHES} batches of {envs_per_gpu} envs per GPU "
-                 f"({RESIDENT_BATCHES * 92 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2) stepped round-robin on one "
-                 "stream, one batch per step"}
+                 f"({RESIDENT_BATCHES * 92 * envs_per_gpu // ENVS_PER_GPU} MB of state vs 126 MB L2), every step passes over all of them"}
     if note:
         cfg["note"] = note
     return cfg
@@ -334,14 +336,15 @@ def run_ours(args, rank, local_rank, world):
     t_idx = 0  # step index of the device-side random agents (per batch it only has to be distinct per step)
 
     def run_steps(n):
-        """n steps round-robin over the resident batches, one launch each, all on the current stream."""
+        """n steps: each one Game.step on every resident env = one launch per resident batch, all on the current stream."""
         nonlocal t_idx
         for _ in range(n):
-            batches[t_idx % RESIDENT_BATCHES].step_random(t_idx)  # ONE launch: fused sampler + Game.step on N envs
+            for g in batches:
+                g.step_random(t_idx)  # ONE launch: fused sampler + Game.step on the batch's N envs
             t_idx += 1
 
-    run_steps(PREROLL * RESIDENT_BATCHES)  # untimed set-up: the steady-state hand mix
-    run_steps(max(W, RESIDENT_BATCHES))    # warm-up
+    run_steps(PREROLL)     # untimed set-up: the steady-state hand mix
+    run_steps(max(W, 3))   # warm-up
     torch.cuda.synchronize()
     for g in batches:
         g.stats_reset()
@@ -350,14 +353,17 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         clocks.start()
     wall0 = time.perf_counter()
-    dev_ms = timed(lambda: run_steps(K))
+    # The K-step region is ~2 ms of device time at the driver's K = 20: it is timed REPEATS times, each time K steps inside
+    # its own barrier + synchronize bracket, and the MEDIAN region is reported (all of them are listed in the line).
+    regions = [timed(lambda: run_steps(K)) for _ in range(REPEATS)]
+    dev_ms = statistics.median(regions)
     wall = time.perf_counter() - wall0
     clock_info = clocks.stop() if rank == 0 else None
 
     # the same K steps with plain stream order between launches: every launch alone on the GPU (the kernel's own duration)
     for g in batches:
         g.set_pipelining(False)
-    unpipelined_ms = timed(lambda: run_steps(K)) / K
+    unpipelined_ms = timed(lambda: run_steps(K)) / (K * RESIDENT_BATCHES)
     for g in batches:
         g.set_pipelining(True)
     stats = batches[0].stats()
@@ -369,7 +375,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- for reference: ONE batch stepped back to back (its 92 MB of state stays in the 126 MB L2)
     g = batches[0]
-    KF = min(K, 64)
+    KF = max(16, min(K, 64))
 
     def one_batch():
         for i in range(KF):
@@ -384,7 +390,7 @@ def run_ours(args, rank, local_rank, world):
     # per-step Python / ctypes issue cost out of the timed region.  The actions are a recording of the device-side
     # random agents, so every one of them is valid for the state it meets.
     main = torch.cuda.current_stream(dev)
-    R = max(1, min(K, 126) // E2E_BATCHES)  # rounds; E = R * E2E_BATCHES steps
+    R = int(os.environ.get("PKB_BENCH_E2E_ROUNDS", "16"))  # steps per batch; E = R * E2E_BATCHES steps in the timed region
     E = R * E2E_BATCHES
     half = (N + 1) // 2
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(E2E_BATCHES)]
@@ -423,15 +429,27 @@ def run_ours(args, rank, local_rank, world):
                 runs[j].step_packed(dev_actions[j], out=dev_out[j])
                 host_out[j][r].copy_(dev_out[j], non_blocking=True)
         graphs.append(gr)
+
+    def replay_all():
+        for st in e2e_streams:
+            st.wait_stream(main)
+        for j in range(E2E_BATCHES):
+            with torch.cuda.stream(e2e_streams[j]):
+                graphs[j].replay()
+        for st in e2e_streams:
+            st.synchronize()
+
+    # warm-up: one untimed replay (graph upload, first touch of the pinned buffers), then the envs go back to where the
+    # recorded actions apply
+    saved = [run.save_state() for run in runs]
+    replay_all()
+    for run, st in zip(runs, saved):
+        run.load_state(st)
+        run.stats_reset()
+    del saved
     barrier()
     t0 = time.perf_counter()
-    for st in e2e_streams:
-        st.wait_stream(main)
-    for j in range(E2E_BATCHES):
-        with torch.cuda.stream(e2e_streams[j]):
-            graphs[j].replay()
-    for st in e2e_streams:
-        st.synchronize()
+    replay_all()
     e2e_s = time.perf_counter() - t0
     # every byte that came back is a step result: R * N env-steps per batch, none rejected
     done_seen = sum(int((ho & 1).sum().item()) for ho in host_out)
@@ -480,7 +498,7 @@ def run_ours(args, rank, local_rank, world):
         ql = q_learning_block(args, rank, local_rank, world, timed)
 
     # ---- max over ranks; NCCL reduction of the statistics vector (the only collective)
-    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms],
+    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms] + regions,
                        dtype=torch.float64, device=dev)
     svec = torch.tensor([stats["steps"], stats["hands"], stats["showdowns"], stats["games"], stats["invalid"],
                          stats["poisoned"]] + stats["payoff_sum"], dtype=torch.float64, device=dev)
@@ -490,14 +508,16 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(svec, op=dist.ReduceOp.SUM)
         dist.all_reduce(s9vec, op=dist.ReduceOp.SUM)
-    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms = vec.tolist()
+    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms = vec.tolist()[:7]
+    regions = vec.tolist()[7:]
     if rank != 0:
         return
 
     bytes_per_launch = algorithmic_bytes_per_step(P) * N
-    avg_launch_s = dev_ms / K / 1e3
+    launches = K * RESIDENT_BATCHES
+    avg_launch_s = dev_ms / launches / 1e3
     achieved = bytes_per_launch / avg_launch_s / 1e9
-    value = N * world * K / (dev_ms / 1e3)
+    value = N * RESIDENT_BATCHES * world * K / (dev_ms / 1e3)
     eval_rate = n_hands * world / (eval_ms / 1e3)
     b9 = algorithmic_bytes_per_step(NINE["num_players"])
     nine_rate = NINE["global_envs"] * K9 / (nine_ms / 1e3)
@@ -525,7 +545,7 @@ def run_ours(args, rank, local_rank, world):
                         "byte per env (done flags + valid mask) D2H to pinned host; "
                         f"{E2E_BATCHES} independent batches in flight on {E2E_BATCHES} streams, each batch's chain of {R} steps "
                         "captured in one CUDA graph and replayed inside the timed region; host synchronises at the end"},
-        "gpu_launches": K,  # one persistent step_warp_kernel launch per step
+        "gpu_launches": launches,  # one persistent step_warp_kernel launch per resident batch and step
         "clocks": clock_info,
         "l2_resident": {"value": N * world / (resident_ms / 1e3), "unit": "env-steps/s",
                         "frac": bytes_per_launch / (resident_ms / 1e3) / 1e9 / peak,
@@ -549,6 +569,9 @@ def run_ours(args, rank, local_rank, world):
                   "invalid": svec[4].item(), "poisoned": svec[5].item(), "payoff_sum": svec[6:6 + P].tolist(),
                   "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},
         "wall_s_timed_region": wall,
+        "timed_regions_ms": regions,
+        "timed_regions_note": f"the K-step region was timed {REPEATS} times (each with its own barrier + synchronize bracket, max over "
+                              "ranks per region); value / ms_per_step / roofline use the median region",
     }
     if ql is not None:
         line["q_learning"] = ql

@@ -271,6 +271,20 @@ class GameBatch:
     def stats_reset(self):
         nat.check(nat.lib().pkb_stats_reset(self._h.ptr, self._stream()))
 
+    # ---- device snapshots ----------------------------------------------------------------------
+    _PLANES = ("credits", "bets", "pending_bets", "payoffs", "minimum_raise_value", "seat_masks", "_meta", "_hand", "_episode")
+
+    def save_state(self) -> dict:
+        """A copy of the whole env state on the device (every plane of pkb_state); see load_state."""
+        return {k: getattr(self, k).clone() for k in self._PLANES}
+
+    def load_state(self, state: dict):
+        """Put back a save_state() copy: the envs continue exactly from there (decks and agent draws are functions of the
+        counters in the state).  Statistics are not part of the state."""
+        for k in self._PLANES:
+            getattr(self, k).copy_(state[k])
+        self.refresh_valid()  # a library call after the foreign writes: the next step launch waits for them
+
     # ---- host snapshots (tests, scalar facade) -----------------------------------------------
     def export(self) -> dict:
         """Host copy of the whole state in the oracle's export layout ([P, N] planes, [N] vectors)."""
