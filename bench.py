@@ -510,6 +510,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(s9vec, op=dist.ReduceOp.SUM)
     dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms = vec.tolist()[:7]
     regions = vec.tolist()[7:]
+    dev_ms = statistics.median(regions)  # median of the per-region maxima over the ranks
     if rank != 0:
         return
 
