@@ -144,6 +144,26 @@ int pkb_step_packed(pkb_env *h, const uint8_t *actions_u4, uint8_t *packed_out, 
  * weights: host u32[7] or NULL.  actions_out: device i32[N] or NULL (the actions taken, for replay). */
 int pkb_step_random(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int32_t *actions_out, uint8_t *flags,
                     uint8_t *valid, void *stream);
+/* ---- PokerGameEnv: envs/game_env.py ---------------------------------------------------------------------------
+ * The reference's RL environment seats the learning agent in seat 0 and lets callables play the other seats.  With the
+ * device-side random agent in those seats (weights as for pkb_step_random; NULL = RandomAgent, agents/random.py:16-17)
+ * both of its entry points are ONE launch each: the kernel keeps stepping an env -- one sampled opponent move per round,
+ * inside the tile -- until the reference's loops would return.  The j-th opponent move of an env inside a call draws
+ * with sampler step index round_base + j - 1 (j = 1, 2, ...; at most PKB_ENV_ROUND_CAP per call, then the env is given
+ * up as poisoned), so callers advance round_base by PKB_ENV_ROUND_CAP from call to call.
+ *
+ * pkb_env_step = PokerGameEnv.step (game_env.py:31-54): actions = device i32[N], seat 0's move per env (PKB_ACTION_SKIP:
+ * leave the env alone); reward = device f64[N] (game_env.py:39, 47; 0.0 for envs not stepped); done = device u8[N]:
+ * bit 0 done, bit 1 hand_over, PKB_F_SKIPPED / PKB_F_INVALID / PKB_F_POISONED as in step flags (a poisoned env reports
+ * done | hand_over so that the caller resets it); valid = device u8[N], the valid mask of the env's active player
+ * afterwards (seat 0 unless the episode is over).  Envs are NOT reset on done (the caller does, as with the reference).
+ * pkb_env_reset = PokerGameEnv.reset (game_env.py:20-29) for the envs selected by env_mask (device u8[N], NULL = all):
+ * Game.reset, then the opponents act until it is seat 0's turn; a game that ends on the way is reset again (:27). */
+#define PKB_ENV_ROUND_CAP 1024
+int pkb_env_step(pkb_env *h, const int32_t *actions, uint32_t round_base, const uint32_t *weights, double *reward,
+                 uint8_t *done, uint8_t *valid, void *stream);
+int pkb_env_reset(pkb_env *h, const uint8_t *env_mask, uint32_t round_base, const uint32_t *weights, uint8_t *valid,
+                  void *stream);
 /* Sampler alone (K5): actions for the CURRENT state, without stepping. */
 int pkb_sample_actions(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int32_t *actions_out, void *stream);
 /* Game.get_valid_actions(player), game.py:339-383.  player < 0: each env's active player. */

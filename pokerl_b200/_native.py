@@ -15,6 +15,7 @@ NUM_MOVES = 7
 F_GAME_OVER, F_HAND_OVER, F_ROUND_OVER, F_INVALID, F_POISONED = 1, 2, 4, 64, 128
 F_SKIPPED, ACTION_SKIP = 32, -2 ** 31  # PKB_F_SKIPPED, PKB_ACTION_SKIP
 NEXT_TURN_CAP = 64
+ENV_ROUND_CAP = 1024
 
 
 class PkbConfig(C.Structure):
@@ -79,6 +80,8 @@ SYMBOLS = {
     "pkb_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pkb_step_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pkb_step_packed": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "pkb_env_step": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "pkb_env_reset": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     "pkb_step_random": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "pkb_sample_actions": (C.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "pkb_valid_actions": (C.c_int, [_vp, _i32, _vp, _vp]),

@@ -85,6 +85,7 @@ class GameBatch:
             self.flags, self.valid = self.outputs[0], self.outputs[1]
             self.actions_taken = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
             self._packed = None
+            self._env_reward = self._env_done = None
 
     # ---- zero-copy state ---------------------------------------------------------------------
     def _wrap_state(self):
@@ -222,6 +223,36 @@ class GameBatch:
     def unpack_outputs(packed):
         """packed uint8 [N] -> (flags uint8 [N] with bits 0-2, valid uint8 [N] seven-bit masks)."""
         return packed & 7, ((packed >> 3) << 1) | 0x41
+
+    def env_step(self, actions, round_base, weights=None, reward=None, done=None, valid=None):
+        """PokerGameEnv.step (envs/game_env.py:31-54) for every env in ONE launch: seat 0 plays actions[i] (int32 [N]), the
+        other seats are played by the device-side random agent until the reference's loops would return.
+        Returns (reward float64 [N], done uint8 [N]: bit 0 done, bit 1 hand_over, flag bits as in step flags, valid)."""
+        if self._env_reward is None:
+            self._env_reward = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+            self._env_done = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        reward = self._env_reward if reward is None else reward
+        done = self._out(done, self._env_done, "done")
+        valid = self._out(valid, self.valid, "valid")
+        actions = torch.as_tensor(actions)
+        if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        if actions.numel() < self.num_envs:
+            raise ValueError(f"need {self.num_envs} actions, got {actions.numel()}")
+        w = None if weights is None else (C.c_uint32 * nat.NUM_MOVES)(*[int(x) for x in weights])
+        nat.check(nat.lib().pkb_env_step(self._h.ptr, nat.ptr(actions), int(round_base) & 0xFFFFFFFF, w, nat.ptr(reward),
+                                         nat.ptr(done), nat.ptr(valid), self._stream()))
+        return reward, done, valid
+
+    def env_reset(self, env_mask=None, round_base=0, weights=None, valid=None):
+        """PokerGameEnv.reset (envs/game_env.py:20-29) for the envs in env_mask (uint8 / bool [N]; None: all) in ONE launch."""
+        if env_mask is not None:
+            env_mask = torch.as_tensor(env_mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        valid = self._out(valid, self.valid, "valid")
+        w = None if weights is None else (C.c_uint32 * nat.NUM_MOVES)(*[int(x) for x in weights])
+        nat.check(nat.lib().pkb_env_reset(self._h.ptr, nat.ptr(env_mask), int(round_base) & 0xFFFFFFFF, w, nat.ptr(valid),
+                                          self._stream()))
+        return valid
 
     def step_random(self, step_idx, weights=None, record_actions=False, flags=None, valid=None):
         """One step with the on-device random agent (uniform, or integer `weights` per move)."""

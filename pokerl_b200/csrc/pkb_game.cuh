@@ -652,4 +652,60 @@ PKB_D bool end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* pa
     return reset_now;
 }
 
+// ---- PokerGameEnv (envs/game_env.py:6-54) as a per-env automaton ---------------------------------------------
+//
+// PokerGameEnv.step plays the agent's action and then lets the other seats act until the hand ends or it is the agent's
+// turn again -- two `while` loops around Game.step.  The env kernel runs those loops round by round for a whole tile:
+// round 0 is the agent's Game.step, every further round one opponent move in the envs whose loops have not returned.
+// env_advance is the control flow between two rounds of ONE env: given the control byte, the flag byte of the Game.step
+// just made, the seat states and the new active player, it returns the next control byte.
+//   bits 0-1 phase (0 returned / idle, 1 inside `while not hand and active != agent` :41-44, 2 inside `while not done and
+//   active != agent` :49-52, 3 inside reset()'s `while active != agent` :24-27), bit 2 another opponent move is due,
+//   bit 3 done, bit 4 hand_over, bit 5 the env was not stepped (PKB_ACTION_SKIP), bit 6 the agent's action was rejected
+//   (ValueError in the reference), bit 7 poisoned (the reference would not terminate / would assert).
+// Transient bits, never stored: AGENT_STEP (in: this was the agent's own step), WRITE_REWARD + REWARD (out: the reward is
+// decided now -- payoffs[agent] if REWARD else 0.0 -- :39 and :47; it must be read NOW, the second loop may end more
+// hands), REDO (out, reset loop: `if done: self.game.reset()` :27).
+enum : uint32_t { EC_PHASE = 3u, EC_LOOP1 = 1u, EC_LOOP2 = 2u, EC_RESET_LOOP = 3u, EC_PENDING = 4u, EC_DONE = 8u, EC_HAND = 16u,
+                  EC_SKIPPED = 32u, EC_REJECTED = 64u, EC_POISONED = 128u,
+                  EC_AGENT_STEP = 0x100u, EC_WRITE_REWARD = 0x200u, EC_REWARD = 0x400u, EC_REDO = 0x800u };
+constexpr int ENV_ROUND_CAP = 1024;  // opponent moves inside one PokerGameEnv call before the env is given up as poisoned
+
+// the byte the caller gets: bit 0 done, bit 1 hand_over, bits 5-7 as above
+PKB_D uint32_t env_out_byte(uint32_t ec) { return (ec >> 3 & 3u) | (ec & (EC_SKIPPED | EC_REJECTED | EC_POISONED)); }
+
+template <int P>
+PKB_D uint32_t env_advance(uint32_t ec_in, uint32_t flags, const Seats& x, int active, bool cap_hit)
+{
+    const bool done_now = (flags & F_GAME_OVER) != 0, hand_now = (flags & F_HAND_OVER) != 0, dead = (flags & F_POISONED) != 0;
+    const uint32_t gave_up = EC_POISONED | EC_DONE | EC_HAND;  // treated as a finished game: the caller's reset re-arms the env
+    const bool agents_turn = active == 0;                      // self.player_agent = 0 (game_env.py:18)
+    uint32_t ec;
+    int phase = (int)(ec_in & EC_PHASE);
+    if (phase == (int)EC_RESET_LOOP) {  // :24-27
+        if (done_now || dead) return EC_RESET_LOOP | EC_REDO;
+        return EC_RESET_LOOP | (!agents_turn && !cap_hit ? EC_PENDING : 0u);
+    }
+    if (ec_in & EC_AGENT_STEP) {  // :34-39
+        if (flags & F_SKIPPED) return EC_SKIPPED | EC_WRITE_REWARD;
+        if (flags & F_INVALID) return EC_REJECTED | EC_WRITE_REWARD;
+        if (dead) return gave_up | EC_WRITE_REWARD;
+        if (done_now || (x.broken & 1u)) return EC_DONE | EC_HAND | EC_WRITE_REWARD | EC_REWARD;  // :37-39
+        ec = (done_now ? EC_DONE : 0u) | (hand_now ? EC_HAND : 0u);
+        phase = (int)EC_LOOP1;
+    } else if (phase == (int)EC_LOOP1) {  // `done, hand, _ = self.game.step(action)` :44
+        if (dead) return gave_up | EC_WRITE_REWARD;
+        ec = (done_now ? EC_DONE : 0u) | (hand_now ? EC_HAND : 0u);
+    } else {  // EC_LOOP2: `done, *_ = self.game.step(action)` :52 -- hand_over keeps the value of the first loop
+        if (dead) return gave_up;
+        ec = (ec_in & EC_HAND) | (done_now ? EC_DONE : 0u);
+    }
+    if (phase == (int)EC_LOOP1) {
+        if (!(ec & EC_HAND) && !agents_turn) return cap_hit ? gave_up | EC_WRITE_REWARD : ec | EC_LOOP1 | EC_PENDING;  // :41
+        ec |= EC_WRITE_REWARD | ((ec & EC_HAND) ? EC_REWARD : 0u);  // :47
+    }
+    if (!(ec & EC_DONE) && !agents_turn) return cap_hit ? ec | gave_up : ec | EC_LOOP2 | EC_PENDING;  // :49
+    return ec;  // :54
+}
+
 }  // namespace pkb

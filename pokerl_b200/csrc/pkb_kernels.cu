@@ -63,6 +63,12 @@ struct StepArgs {
     uint32_t weights[NUM_MOVES];
     uint32_t num_tiles;
     uint32_t wait_prev;  // the launch before this one on the stream is not a step launch of this handle: wait for it
+    // PokerGameEnv mode (step_warp_kernel<P, false, true>): see env_advance
+    uint32_t env_reset;         // 1: PokerGameEnv.reset for the envs selected by env_mask; 0: PokerGameEnv.step
+    uint32_t round_base;        // the j-th opponent move of an env inside this call draws with step index round_base + j - 1
+    const uint8_t* env_mask;    // reset: envs to reset (null: all)
+    double* reward;             // step outputs, one per env
+    uint8_t* env_done;          //   bit 0 done, bit 1 hand_over, bit 5 not stepped (PKB_ACTION_SKIP), bit 6 rejected, bit 7 poisoned
 };
 
 #ifndef PKB_STRIDE_ALIGN
@@ -319,9 +325,13 @@ struct WarpTile {
 };
 static_assert(PKB_WT_SMALL <= 256 && PKB_WT_MID <= 256 && PKB_WT_LARGE <= 256, "list entries hold the slot in 8 bits");
 
-template <int P, bool SAMPLE>
+// ENV (with SAMPLE = false): PokerGameEnv.step / reset in ONE launch -- seat 0 plays the caller's action, the other seats
+// are played by the device sampler, round after round inside the tile, until the reference's loops would return
+// (envs/game_env.py:20-54; the per-env control is env_advance, pkb_game.cuh).
+template <int P, bool SAMPLE, bool ENV = false>
 __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS) step_warp_kernel(const __grid_constant__ StepArgs a)
 {
+    static_assert(!(SAMPLE && ENV), "the env mode takes seat 0's action from the caller");
     using L = WarpTile<P>;
     constexpr int T = L::T;
     constexpr unsigned FULL = 0xffffffffu;
@@ -399,7 +409,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 const size_t env = base + (size_t)(lane + 32 * k);
                 uint32_t b = 254u;
                 if (env < d.n) {
-                    if (a.actions) {
+                    if (ENV && a.env_reset) {  // PokerGameEnv.reset: the byte says whether this env takes part
+                        b = (!a.env_mask || a.env_mask[env]) ? 1u : 0u;
+                    } else if (a.actions) {
                         const int32_t x = a.actions[env];
                         b = x == ACTION_SKIP ? 255u : (x < 0 || x > 253) ? 254u : (uint32_t)x;
                     } else if (a.actions_u8) {
@@ -442,6 +454,29 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
 #endif
         PKB_WTICK(0);
 
+        // PokerGameEnv mode: the passes below run once per ROUND.  Round 0 plays the caller's action for seat 0 (or, for
+        // PokerGameEnv.reset, resets the selected envs); every further round plays one sampled opponent move in the envs
+        // whose reference loop has not returned yet (env_advance).  The per-slot control byte lives in act_row.
+        uint32_t env_round = 0;
+        if (ENV && a.env_reset) {
+            for (int s = lane; s < T; s += 32)
+                if (base + s < d.n && act_row[s]) {  // Game.reset (game_env.py:23)
+                    Seats x{0, 0, 0, 0};
+                    Meta m = unpack_meta(v.meta[s]);
+                    ep[s] += 1;
+                    reset_env<P>(v, s, x, m, a.gc);
+                    store_seats<P>(v, s, x);
+                    m.vm = valid_mask<P>(v, s, m.act);
+                    v.meta[s] = pack_meta(m);
+                    out_v[s] = (uint8_t)m.vm;
+                    out_f[s] = 0;
+                    act_row[s] = (uint8_t)(EC_RESET_LOOP | (m.act != 0 ? EC_PENDING : 0u));
+                } else
+                    act_row[s] = 0;
+            env_round = 1;
+            __syncwarp();
+        }
+        for (bool env_more = true; env_more;) {
         // ---- pass A: every slot
         uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
         const uint32_t n_live = d.n - base < (size_t)T ? (uint32_t)(d.n - base) : (uint32_t)T;  // slots of this tile that are envs
@@ -463,6 +498,11 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     act_row[s] = (uint8_t)action;  // pkb_step_random(actions_out): copied out with the tile's outputs
+                } else if (ENV && env_round) {  // an opponent's move where the env's loop is still running, nothing elsewhere
+                    action = (act_row[s] & EC_PENDING)
+                                 ? (a.use_weights ? pick_weighted(sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.round_base + env_round - 1u), vm, a.weights)
+                                                  : pick_uniform(sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.round_base + env_round - 1u), vm))
+                                 : ACTION_SKIP;
                 } else {
                     action = act_row[s];
                     action = action == 255 ? ACTION_SKIP : action;
@@ -602,6 +642,40 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             n_s = m_s;
         }
 
+            if (!ENV) break;
+            // ---- PokerGameEnv control (envs/game_env.py:20-54): what this round's step means for every env of the tile
+            __threadfence_block();  // the payoff plane is written with plain stores by the lanes of pass D and read here
+            __syncwarp();
+            bool pending = false;
+            for (int s = lane; s < T; s += 32)
+                if (base + s < d.n) {
+                    const size_t env = base + s;
+                    const uint32_t ec_in = env_round == 0 ? (uint32_t)EC_AGENT_STEP : (uint32_t)act_row[s];
+                    uint32_t ec = ec_in;
+                    if (env_round == 0 || (ec_in & EC_PENDING)) {
+                        Seats x = load_seats<P>(v, s);
+                        Meta m = unpack_meta(v.meta[s]);
+                        const bool cap_hit = env_round + 1u >= (uint32_t)ENV_ROUND_CAP;
+                        ec = env_advance<P>(ec_in, out_f[s], x, m.act, cap_hit);
+                        if (ec & EC_REDO) {  // `if done: self.game.reset()` (game_env.py:27)
+                            ep[s] += 1;
+                            reset_env<P>(v, s, x, m, a.gc);
+                            store_seats<P>(v, s, x);
+                            m.vm = valid_mask<P>(v, s, m.act);
+                            v.meta[s] = pack_meta(m);
+                            out_v[s] = (uint8_t)m.vm;
+                            ec = EC_RESET_LOOP | (m.act != 0 && !cap_hit ? EC_PENDING : 0u);
+                        }
+                        if ((ec & EC_WRITE_REWARD) && a.reward) a.reward[env] = (ec & EC_REWARD) ? d.payoffs[env] : 0.0;  // payoffs[agent]: seat 0's row
+                        if (!(ec & EC_PENDING) && !a.env_reset && a.env_done) a.env_done[env] = (uint8_t)env_out_byte(ec);  // step() returns
+                        act_row[s] = (uint8_t)(ec & 255u);
+                    }
+                    pending |= (ec & EC_PENDING) != 0;
+                }
+            env_more = __any_sync(FULL, pending);
+            ++env_round;
+            __syncwarp();
+        }
         // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
         fence_async_smem();
         __syncwarp();
@@ -1092,13 +1166,19 @@ static cudaError_t step_grid(int device, int sm_count, uint64_t n, unsigned* gri
 // One launch per step: a persistent grid of as many blocks as fit the device at once, launched with programmatic stream
 // serialization so that it may start while the previous step launch of the stream is still draining (tiles are handed
 // over one by one through their epoch words, see epoch_wait).
-template <int P, bool SAMPLE>
+template <int P, bool SAMPLE, bool ENV = false>
 static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_count, bool pipelined)
 {
     using L = WarpTile<P>;
     unsigned grid = 0;
     cudaError_t e = step_grid<P>(device, sm_count, a.d.n, &grid, &a.num_tiles);
     if (e != cudaSuccess) return e;
+    if (ENV) {  // same grid as every other step launch of the handle (the launch index is derived from it); if fewer of
+                // this variant's blocks fit an SM, the rest simply start later
+        static int per_sm_env[64] = {0};
+        e = resident_blocks(step_warp_kernel<P, SAMPLE, ENV>, L::THREADS, L::BYTES, device, per_sm_env);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);
@@ -1110,7 +1190,7 @@ static cudaError_t launch_step(StepArgs& a, cudaStream_t s, int device, int sm_c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pipelined ? 1 : 0;  // pkb_set_pipelining(h, 0): plain stream order between step launches
-    return cudaLaunchKernelEx(&cfg, step_warp_kernel<P, SAMPLE>, a);
+    return cudaLaunchKernelEx(&cfg, step_warp_kernel<P, SAMPLE, ENV>, a);
 }
 
 // ---- TMA descriptors (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----
@@ -1326,6 +1406,11 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.actions_u4 = actions_u4;
     a.packed = packed;
     a.actions_out = actions_out;
+    a.env_reset = 0;
+    a.round_base = 0;
+    a.env_mask = nullptr;
+    a.reward = nullptr;
+    a.env_done = nullptr;
     a.flags = flags;
     a.valid = valid;
     a.step_idx = step_idx;
@@ -1356,6 +1441,54 @@ int pkb_step(pkb_env* h, const int32_t* actions, uint8_t* flags, uint8_t* valid,
 int pkb_step_u8(pkb_env* h, const uint8_t* actions, uint8_t* flags, uint8_t* valid, void* stream)
 {
     return step_common(h, false, 0, nullptr, nullptr, actions, nullptr, flags, valid, stream);
+}
+
+// PokerGameEnv.step / reset for every env in one launch (the kernel's env mode)
+static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint8_t* env_mask, uint32_t round_base,
+                      const uint32_t* weights, double* reward, uint8_t* done, uint8_t* valid, void* stream)
+{
+    if (!h) return fail("pkb_env: null handle");
+    if (!reset && !actions) return fail("pkb_env_step: null actions");
+    PKB_CUDA(cudaSetDevice(h->cfg.device));
+    StepArgs a;
+    a.maps = h->maps;
+    a.d = h->d;
+    a.gc = h->gc;
+    a.gc.auto_reset = 0;  // the env decides about resets itself (game_env.py:27 inside reset(), the caller after step())
+    a.actions = actions;
+    a.actions_u8 = nullptr;
+    a.actions_u4 = nullptr;
+    a.packed = nullptr;
+    a.actions_out = nullptr;
+    a.flags = nullptr;
+    a.valid = valid;
+    a.step_idx = 0;
+    a.use_weights = weights ? 1u : 0u;
+    for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
+    a.env_reset = reset ? 1u : 0u;
+    a.round_base = round_base;
+    a.env_mask = env_mask;
+    a.reward = reward;
+    a.env_done = done;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PKB_CUDA(order_on_stream(h, s, true));
+    a.wait_prev = h->last_was_step ? 0u : 1u;
+    cudaError_t e = cudaSuccess;
+    PKB_DISPATCH_P(h->cfg.num_players, e = (launch_step<P, false, true>(a, s, h->cfg.device, h->sm_count, false)));
+    if (e != cudaSuccess) return fail("pkb_env: launch", e);
+    h->last_was_step = true;
+    return 0;
+}
+
+int pkb_env_step(pkb_env* h, const int32_t* actions, uint32_t round_base, const uint32_t* weights, double* reward, uint8_t* done,
+                 uint8_t* valid, void* stream)
+{
+    return env_common(h, false, actions, nullptr, round_base, weights, reward, done, valid, stream);
+}
+
+int pkb_env_reset(pkb_env* h, const uint8_t* env_mask, uint32_t round_base, const uint32_t* weights, uint8_t* valid, void* stream)
+{
+    return env_common(h, true, nullptr, env_mask, round_base, weights, nullptr, nullptr, valid, stream);
 }
 
 int pkb_step_packed(pkb_env* h, const uint8_t* actions_u4, uint8_t* packed_out, void* stream)

@@ -14,6 +14,10 @@ The agent sits in seat 0; the other seats are played by callables `StateView -> 
   Opponents may be `pokerl_b200.agents.RandomAgent` instances: those are sampled on the device by
   `pkb_sample_actions` (no Python per table, no host round trip).  Tables whose episode ended are
   re-armed with `reset(env_mask=done)`.
+  When EVERY opponent is a RandomAgent (with the same weights) the masked loops are not needed at all:
+  `step` and `reset` are ONE launch each (`pkb_env_step` / `pkb_env_reset`), the kernel plays the
+  opponents round by round inside the tile until the reference's loops would return.  No host
+  synchronisation, no per-round torch ops.
 """
 from typing import List, Tuple
 
@@ -35,6 +39,10 @@ class PokerGameEnv(PokerEnv):
         if len(self.agents) != self.game.num_players:
             raise ValueError(f"need {self.game.num_players - 1} opponent agents, got {len(self.agents) - 1}")
         self._round = 0  # counter of batched opponent rounds: the step index of the device-side sampler
+        opponents = self.agents[1:]
+        # every opponent the device-side random agent with one weight vector: one fused launch per step / reset
+        self._fused = (self.game.batched and len(opponents) > 0 and all(isinstance(ag, RandomAgent) for ag in opponents)
+                       and len({ag.weights for ag in opponents}) == 1 and game_config.get('fused', True))
 
     # ---- scalar mode: the reference's control flow, line by line -------------------------------
     def _reset_scalar(self) -> Game.StateView:
@@ -96,7 +104,27 @@ class PokerGameEnv(PokerEnv):
         dead = (flags & nat.F_POISONED) != 0
         return done | dead, hand | dead
 
+    def _fused_round_base(self):
+        base = self._round
+        self._round += nat.ENV_ROUND_CAP  # every call owns its own range of sampler step indices
+        return base
+
+    def _reset_fused(self, env_mask=None):
+        self.game.batch.env_reset(env_mask, self._fused_round_base(), self.agents[1].weights)
+        return self.game.active_state
+
+    def _step_fused(self, action):
+        g, b = self.game, self.game.batch
+        action = torch.as_tensor(action, device=g.device).to(torch.int32)
+        reward, done, _ = b.env_step(action, self._fused_round_base(), self.agents[1].weights)
+        if g.check_actions and bool(((done & nat.F_INVALID) != 0).any().item()):
+            env = int(torch.nonzero(done & nat.F_INVALID)[0].item())
+            raise ValueError('Env %d player 0 invalid move: `%d` (its state is unchanged)' % (env, int(action[env].item())))
+        return g.active_state, reward.clone(), (done & 1) != 0, (done & 2) != 0
+
     def _reset_batched(self, env_mask=None) -> Game.StateView:
+        if self._fused:
+            return self._reset_fused(env_mask)
         b = self.game.batch
         if env_mask is not None:
             env_mask = torch.as_tensor(env_mask, device=self.game.device).bool()
@@ -113,6 +141,8 @@ class PokerGameEnv(PokerEnv):
         return self.game.active_state
 
     def _step_batched(self, action):
+        if self._fused:
+            return self._step_fused(action)
         g, b = self.game, self.game.batch
         action = torch.as_tensor(action, device=g.device).to(torch.int32)
         done, hand = self._step_masked(action)

@@ -98,7 +98,7 @@ def test_batched_env_equals_per_table_reference_flow(torch_cuda, ora):
     from pokerl_b200.envs import PokerGameEnv
     N, P, T = 384, 3, 60
     cfg = dict(num_players=P, start_credits=40, big_blind=4, small_blind=2, seed=9)
-    env = PokerGameEnv(agents=[RandomAgent() for _ in range(P - 1)], num_envs=N, **cfg)
+    env = PokerGameEnv(agents=[RandomAgent() for _ in range(P - 1)], num_envs=N, fused=False, **cfg)  # the masked lockstep loops
     log = []  # (kind, actions [N]) per launch, in order
     inner = env.game.batch.step
 
@@ -177,3 +177,76 @@ def test_q_learning_example_runs(torch_cuda):
     Q, score, stats = mod.run(num_envs=2048, num_steps=12, quiet=True)
     assert Q.shape == (10, 7) and bool(torch_cuda.isfinite(Q).all()) and float(Q.abs().sum()) > 0
     assert score[1] > 0 and stats["invalid"] == 0 and stats["poisoned"] == 0 and stats["hands"] > 0
+
+
+@pytest.mark.parametrize("P,weights", [(3, None), (4, (10, 30, 30, 5, 5, 5, 45)), (2, None)])
+def test_fused_env_step_and_reset_equal_the_reference_loops(torch_cuda, ora, P, weights):
+    """pkb_env_step / pkb_env_reset (ONE launch per PokerGameEnv.step / reset, opponents played by the device sampler
+    inside the kernel) against game_env.py's loops restated over the oracle, table by table: rewards (bit for bit),
+    done / hand_over, the valid mask handed to the agent and the final state.  The j-th opponent move of a table
+    inside call c draws with sampler index c * ENV_ROUND_CAP + j - 1."""
+    torch = torch_cuda
+    from pokerl_b200 import _native as nat
+    from pokerl_b200.agents import RandomAgent
+    from pokerl_b200.envs import PokerGameEnv
+    N, T, seed = 640, 50, 13
+    cfg = dict(num_players=P, start_credits=30, big_blind=4, small_blind=2, seed=seed)
+    env = PokerGameEnv(agents=[RandomAgent(weights) for _ in range(P - 1)], num_envs=N, **cfg)
+    assert env._fused
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    calls = []  # ("reset", mask or None) / ("step", actions, reward, done, hand, valid)
+    state = env.reset()
+    calls.append(("reset", None, state.valid_mask.cpu().numpy()))
+    for t in range(T):
+        assert bool((env.game.batch.active_player == 0).all())
+        a = torch.multinomial(state.valid_actions, 1, generator=gen)[:, 0].to(torch.int32)
+        state, reward, done, hand = env.step(a)
+        calls.append(("step", a.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy(), hand.cpu().numpy()))
+        if bool(done.any()):
+            state = env.reset(env_mask=done)
+            calls.append(("reset", done.cpu().numpy(), state.valid_mask.cpu().numpy()))
+    assert sum(int(c[3].sum()) for c in calls if c[0] == "step") > N  # many episodes ended
+    final = env.game.batch.export()
+    w = None if weights is None else list(weights)
+    for i in range(0, N, 7):
+        ctr = {"base": 0, "j": 0}
+
+        def opponent(mask):
+            a = ora.sample_action(seed, i, ctr["base"] + ctr["j"], mask, w)
+            ctr["j"] += 1
+            return a
+
+        ref = RefEnvOnOracle(ora, [opponent] * (P - 1), env_id=i, **cfg)
+        for c, call in enumerate(calls):
+            ctr["base"], ctr["j"] = c * nat.ENV_ROUND_CAP, 0
+            if call[0] == "reset":
+                if call[1] is None or call[1][i]:
+                    ref.reset()
+                    assert ref.o.valid_mask() == int(call[2][i]), (i, c)
+            else:
+                _, a, reward, done, hand = call
+                r_ref, d_ref, h_ref = ref.step(int(a[i]))
+                assert (bits(reward[i]), bool(done[i]), bool(hand[i])) == (bits(r_ref), d_ref, h_ref), (i, c)
+        snap = ref.o.snapshot()
+        assert [bits(x) for x in final["credits"][:, i]] == [bits(x) for x in snap["credits"]], i
+        assert [bits(x) for x in final["payoffs"][:, i]] == [bits(x) for x in snap["payoffs"]], i
+        assert int(final["hand"][i]) == snap["hand"] and int(final["active"][i]) == snap["active"], i
+        assert int(final["episode"][i]) == ref.o.g.episode, i
+
+
+def test_fused_env_skips_and_rejects(torch_cuda, ora):
+    torch = torch_cuda
+    from pokerl_b200 import _native as nat
+    from pokerl_b200.agents import RandomAgent
+    from pokerl_b200.envs import PokerGameEnv
+    N = 256
+    env = PokerGameEnv(agents=[RandomAgent(), RandomAgent()], num_envs=N, num_players=3, start_credits=50, seed=2)
+    env.reset()
+    before = env.game.batch.export()
+    acts = torch.full((N,), nat.ACTION_SKIP, dtype=torch.int32, device="cuda")
+    reward, done, _ = env.game.batch.env_step(acts, 10 * nat.ENV_ROUND_CAP)
+    assert bool((done == nat.F_SKIPPED).all()) and float(reward.abs().sum()) == 0.0
+    after = env.game.batch.export()
+    assert all(np.array_equal(before[k], after[k]) for k in before)
+    with pytest.raises(ValueError):
+        env.step(torch.full((N,), 1, dtype=torch.int32, device="cuda"))  # CHECK facing the blinds is invalid
