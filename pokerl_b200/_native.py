@@ -113,16 +113,19 @@ def lib():
     if _lib is None:
         path = os.environ.get("PKB_LIB") or _build.LIB  # PKB_LIB: load an experimental build instead
         if not os.environ.get("PKB_LIB"):
-            try:  # (re)build when the library is missing or older than its sources; a no-op when it is fresh
-                _build.build_native()
-            except Exception as e:  # no silent fallback: the CUDA extension IS the product
-                if not os.path.exists(path):
-                    raise ImportError(
-                        f"pokerl_b200: CUDA extension {path} is missing and could not be built ({e}). "
-                        "Run `python -m pokerl_b200._build` on a machine with nvcc.") from e
-                if _build.is_stale():
-                    import warnings
-                    warnings.warn(f"pokerl_b200: {path} is older than its sources and could not be rebuilt ({e})")
+            if not os.path.exists(path) or os.environ.get("PKB_AUTO_REBUILD") == "1":
+                try:  # build when the library is missing (or, on request, older than its sources)
+                    _build.build_native()
+                except Exception as e:  # no silent fallback: the CUDA extension IS the product
+                    if not os.path.exists(path):
+                        raise ImportError(
+                            f"pokerl_b200: CUDA extension {path} is missing and could not be built ({e}). "
+                            "Run `python -m pokerl_b200._build` on a machine with nvcc.") from e
+            if _build.is_stale():
+                # Not rebuilt behind the caller's back: several ranks of one job would all do it at once.  Say so loudly.
+                import warnings
+                warnings.warn(f"pokerl_b200: {path} is older than its sources; run `python -m pokerl_b200._build` "
+                              "(or set PKB_AUTO_REBUILD=1)", RuntimeWarning, stacklevel=2)
         L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
