@@ -45,7 +45,7 @@ ENVS_PER_GPU = 1 << 20
 RESIDENT_BATCHES = 3  # 3 x 92 MB of env state per GPU: larger than the 126 MB L2
 REPEATS = 5           # the K-step timed region is repeated this often; the median is reported
 PREROLL = 64          # untimed steps every batch is rolled forward before anything is measured (steady-state hand mix)
-E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "6"))  # env batches the end-to-end leg keeps in flight
+E2E_BATCHES = int(os.environ.get("PKB_BENCH_E2E_BATCHES", "8"))  # env batches the end-to-end leg keeps in flight (6: 0.80 of `value`, 8 and 12: 0.96-0.97)
 L2_FLUSH_BYTES = 256 << 20
 NINE = dict(num_players=9, start_credits=[20 * (i + 1) for i in range(9)], big_blind=2, small_blind=1, seed=1,
             weights=[10, 30, 30, 5, 5, 5, 45], global_envs=1 << 22)  # BASELINE.json configs[3] / SURVEY 8(d)
@@ -390,7 +390,7 @@ def run_ours(args, rank, local_rank, world):
     # per-step Python / ctypes issue cost out of the timed region.  The actions are a recording of the device-side
     # random agents, so every one of them is valid for the state it meets.
     main = torch.cuda.current_stream(dev)
-    R = int(os.environ.get("PKB_BENCH_E2E_ROUNDS", "16"))  # steps per batch; E = R * E2E_BATCHES steps in the timed region
+    R = int(os.environ.get("PKB_BENCH_E2E_ROUNDS", "32"))  # steps per batch; E = R * E2E_BATCHES steps in the timed region
     E = R * E2E_BATCHES
     half = (N + 1) // 2
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(E2E_BATCHES)]
