@@ -249,3 +249,42 @@ def test_packed_step_equals_plain_step(torch_cuda, ora):
     bad = GameBatch.pack_actions(torch.full((N,), 9, dtype=torch.int32, device=a_batch.device))  # 7..14: rejected
     b_batch.step_packed(bad)
     assert b_batch.stats()["invalid"] == N
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_soak_random_tables_pipelined_against_the_oracle(torch_cuda, ora, seed):
+    """Random table sizes, unequal stacks, blinds and action mixes, 300 fused random-agent steps on 40,000 envs in one
+    tight loop (launches pipelined), with the handle's other entry points called in between (they must order
+    themselves against the overlapping launches); final state bit for bit against the oracle, poisoned envs aside."""
+    torch = torch_cuda
+    from pokerl_b200 import GameBatch
+    from pokerl_b200 import _native as nat
+    rng = np.random.default_rng(100 + seed)
+    P = int(rng.integers(2, 11))
+    start = [int(x) for x in rng.integers(5, 300, P)]
+    bb = int(rng.choice([2, 4, 10]))
+    sb = int(rng.integers(1, bb + 1))
+    weights = None if seed % 2 == 0 else [int(x) for x in rng.integers(1, 50, 7)]
+    N, T = 40000, 300
+    g = GameBatch(N, P, start, bb, sb, seed=seed, env_id_base=7 * seed, auto_reset=True)
+    o = ora.OracleBatch(N, P, start, bb, sb, seed=seed, env_id_base=7 * seed, auto_reset=True)
+    g.reset(); o.reset()
+    poisoned = torch.zeros(N, dtype=torch.bool, device=g.device)
+    for t in range(T):
+        flags, _ = g.step_random(t, weights)
+        poisoned |= (flags & nat.F_POISONED) != 0
+        if t % 37 == 5:
+            g.valid_actions()
+        if t % 53 == 7:
+            g.refresh_valid()
+        if t % 101 == 50:
+            g.stats()
+    o.run_random(0, T, weights)
+    keep = ~poisoned.cpu().numpy()
+    ge, oe = g.export(), o.export()
+    for k in F64_KEYS:
+        a, b = np.ascontiguousarray(ge[k]).view(np.uint64)[..., keep], np.ascontiguousarray(oe[k]).view(np.uint64)[..., keep]
+        assert np.array_equal(a, b), (P, start, bb, sb, weights, k)
+    for k in INT_KEYS:
+        assert np.array_equal(np.asarray(ge[k])[..., keep], np.asarray(oe[k])[..., keep]), (P, start, bb, sb, weights, k)
+    assert g.stats()["steps"] == N * T and (~keep).sum() < N // 100
