@@ -4,7 +4,10 @@ Same learner -- tabular Q over (hand ranking of the agent's cards, move), softma
 uniform exploration (q_learning.py:27-41, 69-93) -- but N tables per GPU advance in lockstep against
 device-side RandomAgents, the hand-ranking feature comes from the showdown evaluator on 2/5/6/7 cards
 (`pkb_hand_features`, q_learning.py:29-33), and the per-step Q updates of all tables are summed into one
-[10, 7] delta that is all-reduced over the ranks (NCCL over NVLink) before it is applied.
+[10, 7] delta that is all-reduced over the ranks (NCCL over NVLink) before it is applied.  The learner sees only
+(hand ranking, valid mask) -- 10 x 128 situations -- so its softmax policy and its max-Q targets are worked out once per
+step for every situation (`policy_tables`) and every table just looks its own up: `PokerGameEnv.step` and `reset` are one
+launch each, the rest is a handful of [N]-sized torch ops.
 
     python examples/q_learning.py --envs 65536 --steps 200
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 examples/q_learning.py --envs 8388608
@@ -23,21 +26,57 @@ from pokerl_b200.envs import PokerGameEnv  # noqa: E402
 
 
 def features(env):
-    """(hand ranking of seat 0's visible cards [N], valid-action matrix bool [N, 7])  -- q_learning.py:29-33"""
+    """(hand ranking of seat 0's visible cards int64 [N], valid-move bit mask int64 [N])  -- q_learning.py:29-33"""
     ranking = (env.game.batch.hand_features(0).long() >> 20) & 0xF
-    mask = env.game.batch.valid_actions(0)
-    valid = ((mask.unsqueeze(1) >> torch.arange(7, device=mask.device)) & 1).bool()
-    return ranking, valid
+    return ranking, env.game.batch.valid_actions(0).long()
 
 
-def predict(Q, s, valid, eps, gen):
-    """softmax(Q[s, valid]) with probability 1 - eps, uniform over the valid moves otherwise (q_learning.py:35-41, 81-82)"""
-    logits = Q[s].masked_fill(~valid, float("-inf"))
-    p_soft = torch.softmax(logits, dim=1)
-    p_unif = valid.double() / valid.sum(dim=1, keepdim=True)
-    explore = torch.rand(s.shape[0], device=s.device, generator=gen) < eps
-    p = torch.where(explore.unsqueeze(1), p_unif, p_soft)
-    return torch.multinomial(p, 1, generator=gen)[:, 0]
+_MASK_BITS = None
+
+
+def mask_bits(dev):
+    """bool [128, 7]: which moves each 7-bit valid mask allows (FOLD is always among them)."""
+    global _MASK_BITS
+    if _MASK_BITS is None or _MASK_BITS.device != dev:
+        m = torch.arange(128, device=dev)
+        _MASK_BITS = ((m.unsqueeze(1) >> torch.arange(7, device=dev)) & 1).bool()
+    return _MASK_BITS
+
+
+def policy_tables(Q, eps):
+    """The learner sees only (hand ranking, valid mask): 10 x 128 distinct situations.  For every one of them the move
+    distribution of q_learning.py:35-41, 81-82 -- softmax(Q[s, valid]) with probability 1 - eps, uniform over the valid
+    moves otherwise -- as a CDF [10, 128, 7], and max over the valid moves of Q[s] [10, 128] (q_learning.py:88)."""
+    valid = mask_bits(Q.device)                                    # [128, 7]
+    logits = Q.unsqueeze(1).masked_fill(~valid.unsqueeze(0), float("-inf"))  # [10, 128, 7]
+    any_valid = valid.any(dim=1).view(1, 128, 1)
+    soft = torch.softmax(torch.where(any_valid, logits, torch.zeros_like(logits)), dim=2)
+    unif = valid.double() / valid.sum(dim=1, keepdim=True).clamp(min=1)
+    p = eps * unif.unsqueeze(0) + (1.0 - eps) * soft
+    best = torch.where(any_valid.squeeze(2), logits.max(dim=2).values, torch.zeros((), dtype=Q.dtype, device=Q.device))
+    return p.cumsum(dim=2), best
+
+
+def predict(cdf, s, mask, gen):
+    """One move per table, drawn from its situation's CDF (the per-table softmax + multinomial of the scalar example)."""
+    row = cdf[s, mask]                                             # [N, 7]
+    u = torch.rand(s.shape[0], device=s.device, dtype=row.dtype, generator=gen).unsqueeze(1) * row[:, -1:]
+    return (u >= row).sum(dim=1).clamp(max=6)
+
+
+def td_update(Q, best, s, u, r, hand, ns, nmask, gamma):
+    """q_learning.py:88-89 for every table, summed into one delta and one visit count per (ranking, move) cell; returns the
+    [2 * 70] vector to be all-reduced."""
+    td_target = r + (~hand).double() * gamma * best[ns, nmask]
+    cell = s * PokerMoves.NUM_MOVES + u
+    n_cells = Q.numel()
+    return torch.cat([torch.bincount(cell, weights=td_target - Q.view(-1)[cell], minlength=n_cells),
+                      torch.bincount(cell, minlength=n_cells).double()])
+
+
+def apply_update(Q, delta, alpha):
+    d, n = delta[:Q.numel()].view_as(Q), delta[Q.numel():].view_as(Q)
+    Q.add_(alpha * d / n.clamp(min=1.0))
 
 
 def run(num_envs=4096, num_steps=100, num_opponents=3, alpha=0.01, gamma=1.0, seed=0, log_every=20, quiet=False):
@@ -45,32 +84,26 @@ def run(num_envs=4096, num_steps=100, num_opponents=3, alpha=0.01, gamma=1.0, se
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     base, n_local = D.shard_envs(num_envs * world, rank, world)
+    # the learner only plays moves out of the valid mask, so the per-step host check for rejected moves is off
     env = PokerGameEnv(agents=[RandomAgent() for _ in range(num_opponents)], num_players=num_opponents + 1,
-                       num_envs=n_local, env_id_base=base, seed=seed, device=local_rank)
+                       num_envs=n_local, env_id_base=base, seed=seed, device=local_rank, check_actions=False)
     gen = torch.Generator(device=dev).manual_seed(seed * 1000003 + rank)
     Q = torch.zeros((HandRanking.NONE, PokerMoves.NUM_MOVES), dtype=torch.float64, device=dev)  # q_learning.py:27
     env.reset()
-    s, valid = features(env)
+    s, mask = features(env)
     score = torch.zeros(2, dtype=torch.float64, device=dev)  # sum of rewards, finished episodes
     for step in range(num_steps):
         eps = 1 - (step / num_steps) ** 2  # q_learning.py:67
-        u = predict(Q, s, valid, eps, gen)
+        cdf, best = policy_tables(Q, eps)
+        u = predict(cdf, s, mask, gen)
         _, r, done, hand = env.step(u.to(torch.int32))
-        if bool(done.any()):
-            env.reset(env_mask=done)
-        ns, nvalid = features(env)
-        # q_learning.py:88-89 for every table, summed into one delta (and one visit count) per cell
-        best_next = Q[ns].masked_fill(~nvalid, float("-inf")).max(dim=1).values
-        td_target = r + (~hand).double() * gamma * best_next
-        cell = s * PokerMoves.NUM_MOVES + u
-        delta = torch.zeros(Q.numel() * 2, dtype=torch.float64, device=dev)
-        delta.index_add_(0, cell, td_target - Q.view(-1)[cell])
-        delta.index_add_(0, Q.numel() + cell, torch.ones_like(td_target))
+        env.reset(env_mask=done)
+        ns, nmask = features(env)
+        delta = td_update(Q, best, s, u, r, hand, ns, nmask, gamma)
         score += torch.stack([r.sum(), done.double().sum()])
         D.all_reduce_sum_(delta)  # the path's only collective
-        d, n = delta[:Q.numel()].view_as(Q), delta[Q.numel():].view_as(Q)
-        Q += alpha * d / n.clamp(min=1.0)
-        s, valid = ns, nvalid
+        apply_update(Q, delta, alpha)
+        s, mask = ns, nmask
         if not quiet and rank == 0 and (step + 1) % log_every == 0:
             tot = score  # this rank's tables
             print(f"step {step + 1}: mean reward per finished episode {tot[0].item() / max(tot[1].item(), 1):+.3f}; "
@@ -93,29 +126,24 @@ def bench_block(envs_per_gpu, rank, local_rank, world, timed, steps=6, num_oppon
     gen = torch.Generator(device=dev).manual_seed(seed * 1000003 + rank)
     Q = torch.zeros((HandRanking.NONE, PokerMoves.NUM_MOVES), dtype=torch.float64, device=dev)
     env.reset()
-    state = {"s": None, "valid": None, "env_steps": 0}
-    state["s"], state["valid"] = features(env)
+    state = {}
+    state["s"], state["mask"] = features(env)
     alpha, gamma = 0.01, 1.0
     score = torch.zeros(2, dtype=torch.float64, device=dev)
 
     def learner_steps(k, eps=0.5):
         for _ in range(k):
-            s, valid = state["s"], state["valid"]
-            u = predict(Q, s, valid, eps, gen)
+            s, mask = state["s"], state["mask"]
+            cdf, best = policy_tables(Q, eps)
+            u = predict(cdf, s, mask, gen)
             _, r, done, hand = env.step(u.to(torch.int32))
             env.reset(env_mask=done)
-            ns, nvalid = features(env)
-            best_next = Q[ns].masked_fill(~nvalid, float("-inf")).max(dim=1).values
-            td_target = r + (~hand).double() * gamma * best_next
-            cell = s * PokerMoves.NUM_MOVES + u
-            delta = torch.zeros(Q.numel() * 2, dtype=torch.float64, device=dev)
-            delta.index_add_(0, cell, td_target - Q.view(-1)[cell])
-            delta.index_add_(0, Q.numel() + cell, torch.ones_like(td_target))
+            ns, nmask = features(env)
+            delta = td_update(Q, best, s, u, r, hand, ns, nmask, gamma)
             score.add_(torch.stack([r.sum(), done.double().sum()]))
             D.all_reduce_sum_(delta)  # NCCL over NVLink: the Q-delta and visit counts of every rank
-            d, n = delta[:Q.numel()].view_as(Q), delta[Q.numel():].view_as(Q)
-            Q.add_(alpha * d / n.clamp(min=1.0))
-            state["s"], state["valid"] = ns, nvalid
+            apply_update(Q, delta, alpha)
+            state["s"], state["mask"] = ns, nmask
 
     learner_steps(2)  # warm-up (allocator, NCCL channel set-up)
     before = env.game.batch.stats()["steps"]

@@ -308,7 +308,8 @@ struct WarpTile {
     static constexpr size_t OFF_OUT_F = OFF_ACT + (size_t)T;    // u8 per slot: the step's flag byte ...
     static constexpr size_t OFF_OUT_V = OFF_OUT_F + (size_t)T;  // ... and valid mask, written to the caller's arrays with the tile
     static constexpr size_t OFF_PAIRS = OFF_OUT_V + (size_t)T;  // u16 (slot | seat << 8): the showing seats of up to 32 hands (P > 2)
-    static constexpr size_t WARP_BYTES = (OFF_PAIRS + (P > 2 ? (size_t)64 * P : 0) + 127) / 128 * 128;
+    static constexpr size_t OFF_PEND = OFF_PAIRS + (P > 2 ? (size_t)64 * P : 0);  // u8 per slot: the env mode's list of slots whose loop has not returned
+    static constexpr size_t WARP_BYTES = (OFF_PEND + (size_t)T + 127) / 128 * 128;
     static constexpr size_t HEADER = 128;
     static constexpr size_t BYTES = HEADER + WARP_BYTES * WARPS;
     static constexpr int THREADS = 32 * WARPS;
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     uint8_t* out_f = buf + L::OFF_OUT_F;
     uint8_t* out_v = buf + L::OFF_OUT_V;
     uint16_t* pairs = reinterpret_cast<uint16_t*>(buf + L::OFF_PAIRS);
+    uint8_t* pend = buf + L::OFF_PEND;
     // whole words of the caller's output arrays can be written at once when both arrays are 4-byte aligned
     const bool out_words = ((reinterpret_cast<uintptr_t>(a.flags) | reinterpret_cast<uintptr_t>(a.valid)) & 3u) == 0;
     View<T> v = tile_view<L>(buf);
@@ -457,33 +459,47 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // PokerGameEnv mode: the passes below run once per ROUND.  Round 0 plays the caller's action for seat 0 (or, for
         // PokerGameEnv.reset, resets the selected envs); every further round plays one sampled opponent move in the envs
         // whose reference loop has not returned yet (env_advance).  The per-slot control byte lives in act_row.
-        uint32_t env_round = 0;
+        // From round 1 on the passes visit only the slots of the PENDING list (built with ballots, like lists E and S).
+        uint32_t env_round = 0, n_pend = 0;
         if (ENV && a.env_reset) {
-            for (int s = lane; s < T; s += 32)
-                if (base + s < d.n && act_row[s]) {  // Game.reset (game_env.py:23)
-                    Seats x{0, 0, 0, 0};
+            for (int s = lane; s < T; s += 32) {
+                bool pending = false;
+                uint32_t vm_now = 0;
+                if (base + s < d.n) {
                     Meta m = unpack_meta(v.meta[s]);
-                    ep[s] += 1;
-                    reset_env<P>(v, s, x, m, a.gc);
-                    store_seats<P>(v, s, x);
-                    m.vm = valid_mask<P>(v, s, m.act);
-                    v.meta[s] = pack_meta(m);
-                    out_v[s] = (uint8_t)m.vm;
-                    out_f[s] = 0;
-                    act_row[s] = (uint8_t)(EC_RESET_LOOP | (m.act != 0 ? EC_PENDING : 0u));
-                } else
-                    act_row[s] = 0;
+                    if (act_row[s]) {  // Game.reset (game_env.py:23)
+                        Seats x{0, 0, 0, 0};
+                        ep[s] += 1;
+                        reset_env<P>(v, s, x, m, a.gc);
+                        store_seats<P>(v, s, x);
+                        m.vm = valid_mask<P>(v, s, m.act);
+                        v.meta[s] = pack_meta(m);
+                        pending = m.act != 0;
+                        act_row[s] = (uint8_t)(EC_RESET_LOOP | (pending ? EC_PENDING : 0u));
+                    } else
+                        act_row[s] = 0;
+                    vm_now = valid_mask<P>(v, s, m.act);  // the valid output of envs no round will touch
+                }
+                out_v[s] = (uint8_t)vm_now;
+                out_f[s] = 0;
+                const uint32_t vote = __ballot_sync(FULL, pending);
+                if (pending) pend[n_pend + (uint32_t)__popc(vote & lanes_below)] = (uint8_t)s;
+                n_pend += (uint32_t)__popc(vote);
+            }
             env_round = 1;
             __syncwarp();
         }
-        for (bool env_more = true; env_more;) {
+        for (bool env_more = !(ENV && a.env_reset) || n_pend != 0; env_more;) {
         // ---- pass A: every slot
         uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
         const uint32_t n_live = d.n - base < (size_t)T ? (uint32_t)(d.n - base) : (uint32_t)T;  // slots of this tile that are envs
+        const uint32_t n_visit = ENV && env_round ? n_pend : (uint32_t)T;
         PKB_UNROLL(PKB_WT_UNROLL_A)
-        for (int s = lane; s < T; s += 32) {
+        for (uint32_t v0 = 0; v0 < n_visit; v0 += 32) {
+            // every slot of the tile in slot order -- or, in the env mode's later rounds, the slots of the pending list
+            const int s = ENV && env_round ? (int)(v0 + lane < n_pend ? pend[v0 + lane] : 0u) : (int)(v0 + lane);
             const size_t env = base + s;
-            const bool live = (uint32_t)s < n_live;
+            const bool live = ENV && env_round ? v0 + lane < n_pend : (uint32_t)s < n_live;
             Ctl c{PC_DONE, 0, 0, 0, 0, 0, 0, 0};
             if (live) {
                 Seats x = load_seats<P>(v, s);
@@ -498,11 +514,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     act_row[s] = (uint8_t)action;  // pkb_step_random(actions_out): copied out with the tile's outputs
-                } else if (ENV && env_round) {  // an opponent's move where the env's loop is still running, nothing elsewhere
-                    action = (act_row[s] & EC_PENDING)
-                                 ? (a.use_weights ? pick_weighted(sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.round_base + env_round - 1u), vm, a.weights)
-                                                  : pick_uniform(sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.round_base + env_round - 1u), vm))
-                                 : ACTION_SKIP;
+                } else if (ENV && env_round) {  // an opponent's move: only envs whose loop is still running are visited
+                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.round_base + env_round - 1u);
+                    action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                 } else {
                     action = act_row[s];
                     action = action == 255 ? ACTION_SKIP : action;
@@ -646,33 +660,41 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             // ---- PokerGameEnv control (envs/game_env.py:20-54): what this round's step means for every env of the tile
             __threadfence_block();  // the payoff plane is written with plain stores by the lanes of pass D and read here
             __syncwarp();
-            bool pending = false;
-            for (int s = lane; s < T; s += 32)
-                if (base + s < d.n) {
+            // the slots that stepped in this round (all of them in round 0, the pending list afterwards); the new pending list
+            // is written in place: at most as many entries as were read, each lane having read its own before the ballot
+            uint32_t n_next = 0;
+            const uint32_t n_stepped = env_round ? n_pend : n_live;
+            for (uint32_t v0 = 0; v0 < n_stepped; v0 += 32) {
+                const bool have = v0 + lane < n_stepped;
+                const int s = env_round ? (int)(have ? pend[v0 + lane] : 0u) : (int)(v0 + lane);
+                bool pending = false;
+                if (have) {
                     const size_t env = base + s;
                     const uint32_t ec_in = env_round == 0 ? (uint32_t)EC_AGENT_STEP : (uint32_t)act_row[s];
-                    uint32_t ec = ec_in;
-                    if (env_round == 0 || (ec_in & EC_PENDING)) {
-                        Seats x = load_seats<P>(v, s);
-                        Meta m = unpack_meta(v.meta[s]);
-                        const bool cap_hit = env_round + 1u >= (uint32_t)ENV_ROUND_CAP;
-                        ec = env_advance<P>(ec_in, out_f[s], x, m.act, cap_hit);
-                        if (ec & EC_REDO) {  // `if done: self.game.reset()` (game_env.py:27)
-                            ep[s] += 1;
-                            reset_env<P>(v, s, x, m, a.gc);
-                            store_seats<P>(v, s, x);
-                            m.vm = valid_mask<P>(v, s, m.act);
-                            v.meta[s] = pack_meta(m);
-                            out_v[s] = (uint8_t)m.vm;
-                            ec = EC_RESET_LOOP | (m.act != 0 && !cap_hit ? EC_PENDING : 0u);
-                        }
-                        if ((ec & EC_WRITE_REWARD) && a.reward) a.reward[env] = (ec & EC_REWARD) ? d.payoffs[env] : 0.0;  // payoffs[agent]: seat 0's row
-                        if (!(ec & EC_PENDING) && !a.env_reset && a.env_done) a.env_done[env] = (uint8_t)env_out_byte(ec);  // step() returns
-                        act_row[s] = (uint8_t)(ec & 255u);
+                    Seats x = load_seats<P>(v, s);
+                    Meta m = unpack_meta(v.meta[s]);
+                    const bool cap_hit = env_round + 1u >= (uint32_t)ENV_ROUND_CAP;
+                    uint32_t ec = env_advance<P>(ec_in, out_f[s], x, m.act, cap_hit);
+                    if (ec & EC_REDO) {  // `if done: self.game.reset()` (game_env.py:27)
+                        ep[s] += 1;
+                        reset_env<P>(v, s, x, m, a.gc);
+                        store_seats<P>(v, s, x);
+                        m.vm = valid_mask<P>(v, s, m.act);
+                        v.meta[s] = pack_meta(m);
+                        out_v[s] = (uint8_t)m.vm;
+                        ec = EC_RESET_LOOP | (m.act != 0 && !cap_hit ? EC_PENDING : 0u);
                     }
-                    pending |= (ec & EC_PENDING) != 0;
+                    if ((ec & EC_WRITE_REWARD) && a.reward) a.reward[env] = (ec & EC_REWARD) ? d.payoffs[env] : 0.0;  // payoffs[agent]: seat 0's row
+                    if (!(ec & EC_PENDING) && !a.env_reset && a.env_done) a.env_done[env] = (uint8_t)env_out_byte(ec);  // step() returns
+                    act_row[s] = (uint8_t)(ec & 255u);
+                    pending = (ec & EC_PENDING) != 0;
                 }
-            env_more = __any_sync(FULL, pending);
+                const uint32_t vote = __ballot_sync(FULL, pending);
+                if (pending) pend[n_next + (uint32_t)__popc(vote & lanes_below)] = (uint8_t)s;
+                n_next += (uint32_t)__popc(vote);
+            }
+            n_pend = n_next;
+            env_more = n_pend != 0;
             ++env_round;
             __syncwarp();
         }

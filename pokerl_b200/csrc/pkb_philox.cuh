@@ -88,9 +88,10 @@ struct Dealer {
     PKB_HDM uint32_t next()
     {
         const int lane = i & 3;
-        if (lane == 0) blk = philox4x32_10(U4{env, hand, episode, (uint32_t)(i >> 2)}, k0, k1);
+        // inline and branch-free: out-of-line calls from code whose lanes have drifted apart run lane group by lane group
+        if (lane == 0) blk = philox4x32_10_inl(U4{env, hand, episode, (uint32_t)(i >> 2)}, k0, k1);
         const uint32_t word = lane == 0 ? blk.x : lane == 1 ? blk.y : lane == 2 ? blk.z : blk.w;
-        const uint32_t id = select_bit(free_mask, mulhi32(word, (uint32_t)(52 - i)));
+        const uint32_t id = select_bit_inl(free_mask, mulhi32(word, (uint32_t)(52 - i)));
         free_mask &= ~(1ull << id);
         ++i;
         return id;

@@ -56,7 +56,7 @@ class Game:
         Scalar mode: same field types as the reference (but `credits`/`bets`/`pending_bets` are host
         copies, not aliases of device memory).  Batched mode: tensors with the env axis first;
         `player_cards` is uint8 [N, 2] and `community_cards` uint8 [N, 5] card values with
-        `num_community` [N] telling how many are visible.
+        `num_community` [N] telling how many are visible; the fields are computed lazily, on first access.
         """
 
         def __init__(self, game: 'Game', player=None):
@@ -74,23 +74,48 @@ class Game:
                 self.pending_bets = game.pending_bets
                 self.minimum_raise_value = game.minimum_raise_value
             else:
-                b = game.batch
+                # Batched views are LAZY: every field is a kernel launch or a pass over N envs, and a training loop that
+                # steps millions of tables looks at one or two of them.  A field is computed from the game's state the
+                # first time it is read and kept from then on (read the fields you need before stepping the game again).
+                self._game, self._fixed_player = game, player
+
+        _LAZY = ("player", "valid_mask", "valid_actions", "turn", "player_cards", "community_cards", "num_community",
+                 "credits", "bets", "pending_bets", "minimum_raise_value")
+
+        def __getattr__(self, name):
+            # only reached for attributes that are not set yet: the lazy fields of a batched view
+            if name.startswith("_") or name not in Game.StateView._LAZY or not self.__dict__.get("_batched", False):
+                raise AttributeError(name)
+            self._materialise(name)
+            return self.__dict__[name]
+
+        def _materialise(self, name):
+            b, d = self._game.batch, self.__dict__
+            if name == "player":
                 act = b.active_player
-                self.player = act if player is None else torch.full_like(act, int(player))
-                mask = b.valid_actions(-1 if player is None else int(player))
-                self.valid_mask = mask
-                self.valid_actions = ((mask.unsqueeze(1) >> torch.arange(7, device=mask.device)) & 1).to(torch.float64)
-                self.turn = b.turn
+                d["player"] = act if self._fixed_player is None else torch.full_like(act, int(self._fixed_player))
+            elif name in ("valid_mask", "valid_actions"):
+                mask = b.valid_actions(-1 if self._fixed_player is None else int(self._fixed_player))
+                d["valid_mask"] = mask
+                d["valid_actions"] = ((mask.unsqueeze(1) >> torch.arange(7, device=mask.device)) & 1).to(torch.float64)
+            elif name in ("turn", "num_community"):
+                turn = b.turn
+                d["turn"] = turn
+                d["num_community"] = torch.where(turn == 0, torch.zeros_like(turn), turn + 2)
+            elif name in ("player_cards", "community_cards"):
                 cards = b.cards()  # [5+2P, N]
                 idx = 5 + 2 * self.player.long()
-                self.player_cards = torch.stack([cards.gather(0, idx.unsqueeze(0))[0],
+                d["player_cards"] = torch.stack([cards.gather(0, idx.unsqueeze(0))[0],
                                                  cards.gather(0, (idx + 1).unsqueeze(0))[0]], dim=1)
-                self.community_cards = cards[:5].t().contiguous()
-                self.num_community = torch.where(self.turn == 0, torch.zeros_like(self.turn), self.turn + 2)
-                self.credits = b.credits.t()
-                self.bets = b.bets.t()
-                self.pending_bets = b.pending_bets.t()
-                self.minimum_raise_value = b.minimum_raise_value
+                d["community_cards"] = cards[:5].t().contiguous()
+            elif name == "credits":
+                d["credits"] = b.credits.t()
+            elif name == "bets":
+                d["bets"] = b.bets.t()
+            elif name == "pending_bets":
+                d["pending_bets"] = b.pending_bets.t()
+            elif name == "minimum_raise_value":
+                d["minimum_raise_value"] = b.minimum_raise_value
 
         @property
         def valid_action_indices(self):
