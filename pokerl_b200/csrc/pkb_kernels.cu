@@ -199,17 +199,15 @@ struct Tally {
 };
 
 // Step outputs of one finished env: flag bits and the valid mask of the new active player, into the tile's two output
-// rows (they leave for the caller's arrays with the tile).  The valid mask is also cached in the meta word: the next step
-// validates its action against it.
+// rows (they leave for the caller's arrays with the tile).  The valid mask is also cached in the meta word (m.vm; the
+// caller stores the word): the next step's sampler draws from it.
 template <int P, class V>
-PKB_D uint32_t write_outputs(V& v, int s, const Ctl& c, uint8_t* out_flags, uint8_t* out_valid, bool skipped = false)
+PKB_D uint32_t write_outputs(const V& v, int s, const Ctl& c, Meta& m, uint8_t* out_flags, uint8_t* out_valid, bool skipped = false)
 {
     const uint32_t f = skipped ? F_SKIPPED : (uint32_t)c.done | (c.invalid ? F_INVALID : 0u) | (c.poisoned ? F_POISONED : 0u);
     out_flags[s] = (uint8_t)f;
-    const uint32_t w = v.meta[s];
-    const uint32_t vm = valid_mask<P>(v, s, unpack_meta(w).act);
-    v.meta[s] = (w & ~(127u << 23)) | vm << 23;
-    out_valid[s] = (uint8_t)vm;
+    m.vm = valid_mask<P>(v, s, m.act);
+    out_valid[s] = (uint8_t)m.vm;
     return f;
 }
 
@@ -529,14 +527,12 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     ++tl.hands;
                     if (end_hand_begin<P>(v, s, x, c, true)) c.pc = PC_SHOWDOWN;  // step_begin has committed
                 }
-                if (!c.invalid) {  // an invalid action changes nothing (game.py:649-651)
-                    store_seats<P>(v, s, x);
-                    v.meta[s] = pack_meta(m);
-                }
+                if (!c.invalid) store_seats<P>(v, s, x);  // an invalid action changes nothing (game.py:649-651)
                 if (c.pc == PC_DONE) {
                     tl.poisoned += (uint32_t)c.poisoned;
-                    write_outputs<P>(v, s, c, out_f, out_v, skipped);
+                    write_outputs<P>(v, s, c, m, out_f, out_v, skipped);
                 }
+                v.meta[s] = pack_meta(m);  // after an invalid action m is what it was, with the valid mask recomputed
             }
 #pragma unroll
             for (int k = 0; k + 1 < NQ; ++k) queue[k] = queue[k + 1];  // next slot's draw to the head
@@ -637,13 +633,13 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                             entry = (uint32_t)s | pack_ctl(c) << 8;
                         }
                         store_seats<P>(v, s, x);
-                        v.meta[s] = pack_meta(m);
                     }
                     if (!again) {
-                        const uint32_t f = write_outputs<P>(v, s, c, out_f, out_v);
+                        const uint32_t f = write_outputs<P>(v, s, c, m, out_f, out_v);
                         tl.games += (f & F_GAME_OVER) ? 1u : 0u;
                         tl.poisoned += (uint32_t)c.poisoned;
                     }
+                    v.meta[s] = pack_meta(m);
                 }
                 const uint32_t vote_e = __ballot_sync(FULL, again), vote_s = __ballot_sync(FULL, again_s);
                 if (again) list_e[m_e + (uint32_t)__popc(vote_e & lanes_below)] = entry;
