@@ -288,3 +288,28 @@ def test_soak_random_tables_pipelined_against_the_oracle(torch_cuda, ora, seed):
     for k in INT_KEYS:
         assert np.array_equal(np.asarray(ge[k])[..., keep], np.asarray(oe[k])[..., keep]), (P, start, bb, sb, weights, k)
     assert g.stats()["steps"] == N * T and (~keep).sum() < N // 100
+
+
+def test_save_and_load_state_resume_exactly(torch_cuda, ora):
+    """GameBatch.save_state / load_state: after putting a snapshot back, the envs replay the same future (decks and
+    agent draws are functions of the counters in the state), whatever happened in between."""
+    torch = torch_cuda
+    from pokerl_b200 import GameBatch
+    g = GameBatch(30000, 4, 60, 2, 1, seed=6, auto_reset=True)
+    g.reset()
+    for t in range(20):
+        g.step_random(t)
+    snap = g.save_state()
+    for t in range(20, 50):
+        g.step_random(t)
+    want = g.export()
+    for t in range(50, 70):  # wander off
+        g.step_random(t)
+    g.load_state(snap)
+    for t in range(20, 50):
+        g.step_random(t)
+    got = g.export()
+    for k in F64_KEYS:
+        assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint64), np.ascontiguousarray(want[k]).view(np.uint64)), k
+    for k in INT_KEYS:
+        assert np.array_equal(got[k], want[k]), k
