@@ -1082,6 +1082,7 @@ struct pkb_env {
     cudaEvent_t order_event;
     bool pipelined;      // step launches may overlap their predecessor's tail (programmatic dependent launch)
     bool last_was_step;  // the handle's previous launch was a step launch (on last_stream)
+    unsigned long long last_capture;  // id of the stream capture that launch was recorded into (0: launched live)
 };
 
 static thread_local std::string g_error;
@@ -1132,6 +1133,23 @@ static cudaError_t order_on_stream(pkb_env* h, cudaStream_t s, bool step_launch 
     h->last_stream = s;
     h->has_last = true;
     return e;
+}
+
+// Does the step launch about to be issued on `s` follow, at run time, the handle's previous step launch?  Only then may
+// it skip griddepcontrol.wait.  A launch recorded into a CUDA graph follows its recorded predecessor only if that one
+// went into the SAME capture; the first launch of a capture, and the first live launch after one, wait.
+static uint32_t step_must_wait(pkb_env* h, cudaStream_t s)
+{
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(s, &status, &id) != cudaSuccess) {
+        (void)cudaGetLastError();
+        status = cudaStreamCaptureStatusNone;
+    }
+    const unsigned long long now = status == cudaStreamCaptureStatusActive ? id : 0ull;
+    const bool same_context = now == h->last_capture;
+    h->last_capture = now;
+    return h->last_was_step && same_context ? 0u : 1u;
 }
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -1441,7 +1459,7 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     // produced, so it keeps plain stream order.  (Other work the caller puts on the stream BETWEEN two pkb_step_random
     // calls must not write the handle's state; pkb_refresh_valid / pkb_reset between them are fine.)
     const bool ahead = sample && h->pipelined;
-    a.wait_prev = h->last_was_step ? 0u : 1u;
+    a.wait_prev = step_must_wait(h, s);
     cudaError_t e = cudaSuccess;
     PKB_DISPATCH_P(h->cfg.num_players,
                    e = sample ? launch_step<P, true>(a, s, h->cfg.device, h->sm_count, ahead)
@@ -1490,7 +1508,7 @@ static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint
     a.env_done = done;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PKB_CUDA(order_on_stream(h, s, true));
-    a.wait_prev = h->last_was_step ? 0u : 1u;
+    a.wait_prev = step_must_wait(h, s);
     cudaError_t e = cudaSuccess;
     PKB_DISPATCH_P(h->cfg.num_players, e = (launch_step<P, false, true>(a, s, h->cfg.device, h->sm_count, false)));
     if (e != cudaSuccess) return fail("pkb_env: launch", e);

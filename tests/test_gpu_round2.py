@@ -313,3 +313,37 @@ def test_save_and_load_state_resume_exactly(torch_cuda, ora):
         assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint64), np.ascontiguousarray(want[k]).view(np.uint64)), k
     for k in INT_KEYS:
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_step_launches_replayed_from_a_cuda_graph(torch_cuda, ora):
+    """A loop of pkb_step_random launches captured in a CUDA graph (programmatic edges between them) and replayed: the
+    launch index is derived on the device and the first launch of a replay waits for whatever precedes it, so every
+    replay continues exactly where the stream left the envs."""
+    torch = torch_cuda
+    from pokerl_b200 import GameBatch
+    N, P, K = 1 << 17, 2, 10
+    g = GameBatch(N, P, 100, 2, 1, seed=12, auto_reset=True)
+    o = ora.OracleBatch(N, P, 100, 2, 1, seed=12, auto_reset=True)
+    g.reset(); o.reset()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        side.wait_stream(torch.cuda.current_stream())
+        g.refresh_valid()  # move the handle to the capture stream before capturing (a stream switch needs an event)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for t in range(K):
+            g.step_random(t)
+    # the capture itself executes nothing
+    states_equal(g, o, "after capture")
+    for rep in range(3):
+        graph.replay()
+        if rep == 1:
+            torch.cuda.synchronize()
+            g.valid_actions()  # a live call between two replays
+        o.run_random(0, K)
+    torch.cuda.synchronize()
+    states_equal(g, o, "after three replays")
+    g.step_random(99)  # and a live launch after the graph
+    o.run_random(99, 1)
+    states_equal(g, o, "live launch after the replays")
