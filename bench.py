@@ -607,9 +607,9 @@ def run_ours(args, rank, local_rank, world):
                                      "unpipelined_launch_us": nine_unpipelined_ms * 1e3, "traffic": ncu_traffic("step_kernel_p9")},
                         "stats": dict(zip(("steps", "hands", "showdowns", "games", "invalid", "poisoned"), s9vec.tolist()))},
         "hand_evals": {"metric": "hand_evals_per_sec", "value": eval_rate, "unit": "7-card evals/s", "hands": n_hands,
-                       "roofline": {"bound": "hbm", "kernel": "pkb::eval_masks_hash_kernel", "achieved": 12 * eval_rate / world / 1e9,
+                       "roofline": {"bound": "hbm", "kernel": "pkb::eval_masks_fast_kernel", "achieved": 12 * eval_rate / world / 1e9,
                                     "peak": peak, "unit": "GB/s", "frac": 12 * eval_rate / world / 1e9 / peak,
-                                    "traffic": ncu_traffic("eval_masks_hash_kernel"), "algorithmic_bytes_per_eval": 12}},
+                                    "traffic": ncu_traffic("eval_masks_fast_kernel"), "algorithmic_bytes_per_eval": 12}},
         "stats": {"steps": svec[0].item(), "hands": svec[1].item(), "showdowns": svec[2].item(), "games": svec[3].item(),
                   "invalid": svec[4].item(), "poisoned": svec[5].item(), "payoff_sum": svec[6:6 + P].tolist(),
                   "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},

@@ -219,7 +219,9 @@ PKB_HD uint32_t flush_table_entry(uint32_t fl)
 
 // host side: fills nf[EVAL_NF_SIZE] (every seven-card rank multiset -> its value without the special cases) and returns
 // the number of multisets written; 0 if two multisets collide (the keys would be wrong)
-inline uint32_t eval_nf_table_fill(uint32_t* nf)
+// wheel_as_straight: rank-wheel multisets (A,2,3,4,5 present, six absent) get STRAIGHT[5], what judger.py:86-88 returns
+// for them unless suit X's lowest run is exactly 5-4-3-2 (the streaming form's tables; eval7_hash3 wants the plain value)
+inline uint32_t eval_nf_table_fill(uint32_t* nf, bool wheel_as_straight = false)
 {
     for (uint32_t i = 0; i < EVAL_NF_SIZE; ++i) nf[i] = 0;
     uint32_t written = 0;
@@ -227,7 +229,7 @@ inline uint32_t eval_nf_table_fill(uint32_t* nf)
     bool ok = true;
     // depth-first over the counts of the 13 ranks, 0..4 each, 7 in all
     struct Rec {
-        static void go(int r, int left, int* cnt, uint32_t* nf, uint32_t& written, bool& ok)
+        static void go(int r, int left, int* cnt, uint32_t* nf, uint32_t& written, bool& ok, bool wheel_as_straight)
         {
             if (r == 13) {
                 if (left) return;
@@ -249,18 +251,20 @@ inline uint32_t eval_nf_table_fill(uint32_t* nf)
                     }
                 }
                 if (load[0] >= 5 || load[1] >= 5 || load[2] >= 5 || load[3] >= 5 || nf[key]) { ok = false; return; }
-                nf[key] = eval_mask52_impl(m, false);
+                // rank wheel: A,2,3,4,5 present and six absent (rank-set bits 12, 0, 1, 2, 3 and 4)
+                const bool rank_wheel = cnt[12] && cnt[0] && cnt[1] && cnt[2] && cnt[3] && !cnt[4];
+                nf[key] = wheel_as_straight && rank_wheel ? (HR_STRAIGHT << 20) | 4u : eval_mask52_impl(m, false);
                 ++written;
                 return;
             }
             for (int c = 0; c <= 4 && c <= left; ++c) {
                 cnt[r] = c;
-                go(r + 1, left - c, cnt, nf, written, ok);
+                go(r + 1, left - c, cnt, nf, written, ok, wheel_as_straight);
             }
             cnt[r] = 0;
         }
     };
-    Rec::go(0, 7, cnt, nf, written, ok);
+    Rec::go(0, 7, cnt, nf, written, ok, wheel_as_straight);
     return ok ? written : 0u;
 }
 
@@ -358,6 +362,109 @@ PKB_HD uint32_t eval7_hash3(uint64_t m, const uint32_t* __restrict__ klo, const 
     r = (rank_wheel && !run_is_wheel_low) ? (HR_STRAIGHT << 20) | 4u : r;      // :86-88
     r = (run_is_wheel_low && fl && (fl & 1u)) ? (HR_STRAIGHT_FLUSH << 20) | 4u : r;  // :83-85 (raw bit 0 = the ace)
     return r;
+}
+
+// ---- streaming form of the perfect hash (the batch kernel eval_masks_fast_kernel) ------------------------------------
+//
+// eval7_hash3 above spends most of its ~115 instructions per hand on the flush suit and the special cases, which 95 % of
+// random seven-card hands do not have.  This form computes ONLY the common case and says when it does not apply:
+//   * the two key tables carry, above the 23-bit key sum, the number of cards of the slice part (bit 24 up; the high
+//     part adds a bias of 3), so the sum over a suit's two entries has bit 27 set iff the suit holds five or more cards,
+//     and the sum over all eight entries has (cards + 12) above bit 24: flush test and seven-card test are by-products
+//     of the key sum;
+//   * a low-part entry also carries bit 31 when the part holds 2,3,4,5 and no six (only then can the lowest run of a
+//     suit be exactly 5-4-3-2, the one thing about a hand's suits that the special cases of judger.py:83-88 look at when
+//     no suit holds five cards); two suits cannot both have it in seven cards, so it survives in the sum and fails the
+//     seven-card test.  Every other rank wheel (A,2,3,4,5 present, six absent) IS STRAIGHT[5], so the value table says so;
+//   * the first level of the displacement hash is one BYTE per bucket, bucket = (sum * 0x9E3779B1) >> 18 (16,384 buckets
+//     of ~3 multisets each instead of eval7_hash3's runs of 256 consecutive key sums, which hold up to 191), small enough
+//     for shared memory; both hash levels work on the whole 32-bit sum (the card count above the key is a constant for
+//     seven-card hands), so a mask with any number of bits set still indexes inside the tables.
+// A hand is RARE if a suit holds >= 5 cards or 2,3,4,5 without the six, or if it does not have exactly seven cards; the
+// caller ranks rare hands with eval_mask52_sel (the batch kernel queues them per warp and ranks 32 at a time).  For every
+// other mask the value read from the table IS eval_mask52(m): checked on all C(52,7) hands (hostcheck) and on the GPU.
+constexpr uint32_t EVAL_FAST_BUCKETS = 1u << 14;
+constexpr uint32_t EVAL_FAST_FLUSH_BIT = 1u << 27;      // of a per-suit sum: the suit holds >= 5 cards
+constexpr uint32_t EVAL_FAST_SEVEN = (7u + 12u) << 24;  // bits 24.. of the sum over all suits when the mask has 7 cards
+constexpr uint32_t EVAL_FAST_LOWRUN_BIT = 1u << 31;     // of a low-part entry: 2,3,4,5 present, six absent (raw bits 1-4 set, 5 clear)
+inline uint32_t fast_klo_entry(uint32_t x)
+{
+    return raw_key_sum(x & 127u) + ((uint32_t)popc32(x & 127u) << 24) + ((x & 0x3Eu) == 0x1Eu ? EVAL_FAST_LOWRUN_BIT : 0u);
+}
+inline uint32_t fast_khi_entry(uint32_t x) { return raw_key_sum((x & 63u) << 7) + ((uint32_t)(popc32(x & 63u) + 3) << 24); }
+PKB_HD uint32_t fast_bucket(uint32_t sum) { return (sum * 0x9E3779B1u) >> 18; }
+PKB_HD uint32_t fast_slot(uint32_t sum, uint32_t disp) { return (sum * (0x85EBCA6Bu + 2u * disp)) >> 16; }
+
+// host side: nf (from eval_nf_table_fill(nf, true)) -> disp[EVAL_FAST_BUCKETS], dense[EVAL_DENSE_SIZE];
+// false if some bucket found no multiplier
+inline bool eval_fast_table_fill(const uint32_t* nf, uint8_t* disp, uint32_t* dense)
+{
+    constexpr uint32_t NB = EVAL_FAST_BUCKETS;
+    uint32_t* count = new uint32_t[NB];
+    uint32_t* start = new uint32_t[NB + 1];
+    for (uint32_t b = 0; b < NB; ++b) count[b] = 0;
+    uint32_t total_keys = 0;
+    for (uint32_t k = 0; k < EVAL_NF_SIZE; ++k)
+        if (nf[k]) { ++count[fast_bucket(k + EVAL_FAST_SEVEN)]; ++total_keys; }
+    start[0] = 0;
+    for (uint32_t b = 0; b < NB; ++b) start[b + 1] = start[b] + count[b];
+    uint32_t* members = new uint32_t[total_keys ? total_keys : 1];
+    uint32_t* fill = new uint32_t[NB];
+    for (uint32_t b = 0; b < NB; ++b) fill[b] = start[b];
+    for (uint32_t k = 0; k < EVAL_NF_SIZE; ++k)
+        if (nf[k]) members[fill[fast_bucket(k + EVAL_FAST_SEVEN)]++] = k;
+    uint32_t maxc = 0;
+    for (uint32_t b = 0; b < NB; ++b) maxc = count[b] > maxc ? count[b] : maxc;
+    bool* used = new bool[EVAL_DENSE_SIZE];
+    for (uint32_t i = 0; i < EVAL_DENSE_SIZE; ++i) { used[i] = false; dense[i] = 0; }
+    for (uint32_t b = 0; b < NB; ++b) disp[b] = 0;
+    uint32_t* slots = new uint32_t[maxc ? maxc : 1];
+    bool ok = true;
+    for (uint32_t c = maxc; c >= 1 && ok; --c)  // largest buckets first
+        for (uint32_t b = 0; b < NB && ok; ++b) {
+            if (count[b] != c) continue;
+            const uint32_t* keys = members + start[b];
+            uint32_t d = 0;
+            for (; d < 256u; ++d) {
+                bool fits = true;
+                for (uint32_t a = 0; a < c && fits; ++a) {
+                    slots[a] = fast_slot(keys[a] + EVAL_FAST_SEVEN, d);
+                    if (used[slots[a]]) fits = false;
+                    for (uint32_t e = 0; e < a && fits; ++e) fits = slots[e] != slots[a];
+                }
+                if (fits) break;
+            }
+            if (d == 256u) { ok = false; break; }
+            disp[b] = (uint8_t)d;
+            for (uint32_t a = 0; a < c; ++a) {
+                used[slots[a]] = true;
+                dense[slots[a]] = nf[keys[a]];
+            }
+        }
+    delete[] count;
+    delete[] start;
+    delete[] members;
+    delete[] fill;
+    delete[] used;
+    delete[] slots;
+    return ok;
+}
+
+// the common case.  klo/khi: fast_klo_entry / fast_khi_entry tables with entry x at [x * stride + lane] (the batch kernel
+// keeps one copy per lane, stride 32, so that no two lanes of a warp ever meet in a shared-memory bank; the host check
+// passes stride 1, lane 0).  Returns the table value; *rare != 0 means the value must not be used.
+PKB_HD uint32_t eval7_fast(uint64_t m, const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi, uint32_t stride, uint32_t lane,
+                           const uint8_t* __restrict__ disp, const uint32_t* __restrict__ dense, uint32_t* rare)
+{
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32), mid = (uint32_t)(m >> 26);
+    const uint32_t s0 = klo[(lo & 127u) * stride + lane] + khi[(lo >> 7 & 63u) * stride + lane];
+    const uint32_t s1 = klo[(lo >> 13 & 127u) * stride + lane] + khi[(lo >> 20 & 63u) * stride + lane];
+    const uint32_t s2 = klo[(mid & 127u) * stride + lane] + khi[(mid >> 7 & 63u) * stride + lane];
+    const uint32_t s3 = klo[(hi >> 7 & 127u) * stride + lane] + khi[(hi >> 14 & 63u) * stride + lane];
+    const uint32_t sum = s0 + s1 + s2 + s3;
+    const uint32_t v = dense[fast_slot(sum, disp[fast_bucket(sum)])];
+    *rare = ((s0 | s1 | s2 | s3) & EVAL_FAST_FLUSH_BIT) | ((sum ^ EVAL_FAST_SEVEN) >> 24);
+    return v;
 }
 
 // ---- select form of eval_mask52 (the step kernels) -----------------------------------------------------

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -957,6 +958,121 @@ eval_masks_hash_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t*
     }
 }
 
+// ---- the streaming form (pkb_eval.cuh eval7_fast): every table in shared memory, rare hands queued per warp ----------
+//
+// One 1024-thread block per SM.  Shared memory holds: the two key tables with one copy per lane (entry x of lane l at
+// x * 128 + l * 4: the eight key look-ups of a hand never meet in a bank), the byte-wide first hash level, the 65,536
+// value slots as 16-bit class numbers and the class -> packed value table (the seven-card values without a flush are
+// ~3,500 distinct words).  A hand costs eight conflict-free and three scattered shared-memory loads and no global
+// gather; eval7_hash3's kernel above spent its time in the L1 (three global gathers plus bank conflicts, l1tex 86 %).
+// A warp trip ranks 32 x EVAL_FAST_HPT hands (two 128-bit loads and two 64-bit stores per lane).  Hands that the common
+// case does not cover (a flush suit, the 5-4-3-2 low run, not seven cards: ~3 % of random hands) leave a wrong word in
+// `out`; their index goes to the warp's ring buffer (ballot + popcount prefix), and whenever 32 are waiting the warp
+// ranks them together with the select evaluator and overwrites the words -- so the branch-free evaluator always runs on
+// full warps instead of inside a divergent branch (in place it costs 2x: 116 G against 235 G evals/s measured).
+struct EvalFastTables {
+    const uint32_t* klo;      // [128]   fast_klo_entry
+    const uint32_t* khi;      // [64]    fast_khi_entry
+    const uint8_t* disp;      // [EVAL_FAST_BUCKETS]
+    const uint16_t* dense16;  // [EVAL_DENSE_SIZE] slot -> class
+    const uint32_t* vals;     // [nvals] class -> packed value
+    uint32_t nvals;
+};
+constexpr int EVAL_FAST_THREADS = 1024, EVAL_FAST_HPT = 4, EVAL_FAST_QSIZE = 256;  // ring >= 31 + 32 * HPT entries
+constexpr uint64_t EVAL_FAST_MIN_HANDS = 1ull << 17;  // below this the staging of the tables (~190 KB per block) does not pay
+static size_t eval_fast_smem(uint32_t nvals)
+{
+    return 128 * 32 * 4 + 64 * 32 * 4 + EVAL_FAST_BUCKETS + (EVAL_FAST_THREADS / 32) * EVAL_FAST_QSIZE * 4 + EVAL_DENSE_SIZE * 2 + (size_t)nvals * 4;
+}
+
+PKB_D uint32_t lds_off(const void* base, uint32_t off) { return *reinterpret_cast<const uint32_t*>(static_cast<const char*>(base) + off); }
+
+// eval7_fast on the device: byte offsets into the per-lane copies of the key tables
+PKB_D uint32_t eval7_fast_dev(uint32_t lo, uint32_t hi, const uint32_t* s_klo, const uint32_t* s_khi, uint32_t lane4, const uint8_t* s_disp,
+                              const uint16_t* s_dense16, const uint32_t* s_vals, uint32_t& rare)
+{
+    const uint32_t mid = __funnelshift_r(lo, hi, 19);  // bits 26.. of the mask at bit 7
+    const uint32_t s0 = lds_off(s_klo, ((lo << 7) & 0x3F80u) | lane4) + lds_off(s_khi, (lo & 0x1F80u) | lane4);
+    const uint32_t s1 = lds_off(s_klo, ((lo >> 6) & 0x3F80u) | lane4) + lds_off(s_khi, ((lo >> 13) & 0x1F80u) | lane4);
+    const uint32_t s2 = lds_off(s_klo, (mid & 0x3F80u) | lane4) + lds_off(s_khi, ((hi << 6) & 0x1F80u) | lane4);
+    const uint32_t s3 = lds_off(s_klo, (hi & 0x3F80u) | lane4) + lds_off(s_khi, ((hi >> 7) & 0x1F80u) | lane4);
+    const uint32_t sum = s0 + s1 + s2 + s3;
+    rare = ((s0 | s1 | s2 | s3) & EVAL_FAST_FLUSH_BIT) | ((sum ^ EVAL_FAST_SEVEN) >> 24);
+    return s_vals[s_dense16[fast_slot(sum, s_disp[fast_bucket(sum)])]];
+}
+
+// ranks the `count` (<= 32) hands whose indices wait at q[head ..] with the select evaluator; one out-of-line copy
+__device__ __noinline__ void eval_fast_drain(const uint32_t* q, uint32_t head, uint32_t count, const uint64_t* __restrict__ masks,
+                                             uint32_t* __restrict__ out)
+{
+    __syncwarp();  // the ring's entries, and the words the common case stored for these hands, come first
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane < count) {
+        const uint32_t idx = q[(head + lane) & (EVAL_FAST_QSIZE - 1)];
+        out[idx] = eval_mask52_sel(masks[idx]);
+    }
+}
+
+// masks 16-byte aligned, out 8-byte aligned, n < 2^32
+__global__ void __launch_bounds__(EVAL_FAST_THREADS, 1)
+eval_masks_fast_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t* __restrict__ out, EvalFastTables t)
+{
+    constexpr int THREADS = EVAL_FAST_THREADS, WARPS = THREADS / 32, HPT = EVAL_FAST_HPT, QSIZE = EVAL_FAST_QSIZE;
+    extern __shared__ __align__(128) uint8_t fast_smem[];
+    uint32_t* s_klo = reinterpret_cast<uint32_t*>(fast_smem);                    // [128][32]
+    uint32_t* s_khi = s_klo + 128 * 32;                                         // [64][32]
+    uint8_t* s_disp = reinterpret_cast<uint8_t*>(s_khi + 64 * 32);              // [EVAL_FAST_BUCKETS]
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_disp + EVAL_FAST_BUCKETS);  // [WARPS][QSIZE]
+    uint16_t* s_dense16 = reinterpret_cast<uint16_t*>(s_queue + WARPS * QSIZE);  // [EVAL_DENSE_SIZE]
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_dense16 + EVAL_DENSE_SIZE);  // [nvals]
+    for (int i = threadIdx.x; i < 128 * 32; i += THREADS) s_klo[i] = t.klo[i >> 5];
+    for (int i = threadIdx.x; i < 64 * 32; i += THREADS) s_khi[i] = t.khi[i >> 5];
+    for (int i = threadIdx.x; i < (int)EVAL_FAST_BUCKETS / 16; i += THREADS) reinterpret_cast<uint4*>(s_disp)[i] = reinterpret_cast<const uint4*>(t.disp)[i];
+    for (int i = threadIdx.x; i < (int)EVAL_DENSE_SIZE / 8; i += THREADS) reinterpret_cast<uint4*>(s_dense16)[i] = reinterpret_cast<const uint4*>(t.dense16)[i];
+    for (int i = threadIdx.x; i < (int)t.nvals; i += THREADS) s_vals[i] = t.vals[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, lane4 = lane * 4, lt = (1u << lane) - 1u;
+    const uint64_t trips = n / (32 * HPT), wstride = (uint64_t)gridDim.x * WARPS;
+    uint32_t head = 0, tail = 0;
+    uint32_t* q = s_queue + w * QSIZE;
+    for (uint64_t trip = (uint64_t)blockIdx.x * WARPS + w; trip < trips; trip += wstride) {
+        const uint64_t pair0 = trip * (16 * HPT) + lane;  // this lane's pairs of hands: pair0 + 32 j
+        ulonglong2 m[HPT / 2];
+#pragma unroll
+        for (int j = 0; j < HPT / 2; ++j) m[j] = reinterpret_cast<const ulonglong2*>(masks)[pair0 + 32 * j];
+        uint32_t r[HPT], rare[HPT];
+#pragma unroll
+        for (int j = 0; j < HPT / 2; ++j) {
+            r[2 * j] = eval7_fast_dev((uint32_t)m[j].x, (uint32_t)(m[j].x >> 32), s_klo, s_khi, lane4, s_disp, s_dense16, s_vals, rare[2 * j]);
+            r[2 * j + 1] = eval7_fast_dev((uint32_t)m[j].y, (uint32_t)(m[j].y >> 32), s_klo, s_khi, lane4, s_disp, s_dense16, s_vals, rare[2 * j + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < HPT / 2; ++j) reinterpret_cast<uint2*>(out)[pair0 + 32 * j] = make_uint2(r[2 * j], r[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, rare[j] != 0);
+            if (rare[j]) q[(tail + __popc(bal & lt)) & (QSIZE - 1)] = (uint32_t)(2 * (pair0 + 32 * (j / 2)) + (j & 1));
+            tail += __popc(bal);
+        }
+        while (tail - head >= 32) {
+            eval_fast_drain(q, head, 32, masks, out);
+            head += 32;
+        }
+    }
+    // the last n % (32 HPT) hands: the block's first warp queues them all
+    if (blockIdx.x == 0 && w == 0)
+        for (uint64_t i = trips * (32 * HPT) + lane; i < n + lane; i += 32) {  // n + lane: every lane makes the same number of trips
+            const uint32_t bal = __ballot_sync(0xffffffffu, i < n);
+            if (i < n) q[(tail + __popc(bal & lt)) & (QSIZE - 1)] = (uint32_t)i;
+            tail += __popc(bal);
+        }
+    while (tail != head) {
+        const uint32_t count = tail - head < 32 ? tail - head : 32;
+        eval_fast_drain(q, head, count, masks, out);
+        head += count;
+    }
+}
+
 __constant__ uint64_t c_binom[53][8];  // C(n, k) for n <= 52, k <= 7
 
 // index -> k-subset of {0..51} in colex order (combinatorial number system)
@@ -1754,18 +1870,95 @@ static cudaError_t ensure_eval_hash_tables(EvalHashTables* out)
     return cudaSuccess;
 }
 
+// builds the streaming evaluator's tables on the current device the first time it runs there (host: ~50 ms)
+static cudaError_t ensure_eval_fast_tables(EvalFastTables* out)
+{
+    static EvalFastTables tabs[64];
+    static bool ready[64] = {false};
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!ready[dev]) {
+        uint32_t* nf = static_cast<uint32_t*>(malloc((size_t)EVAL_NF_SIZE * 4));
+        uint32_t* dense = static_cast<uint32_t*>(malloc((size_t)EVAL_DENSE_SIZE * 4 * 2));  // values, then a sorted copy
+        // one upload: klo | khi | vals (<= EVAL_DENSE_SIZE) | dense16 | disp
+        const size_t words = 128 + 64 + EVAL_DENSE_SIZE + EVAL_DENSE_SIZE / 2 + EVAL_FAST_BUCKETS / 4;
+        uint32_t* host = static_cast<uint32_t*>(malloc(words * 4));
+        if (!nf || !dense || !host) {
+            free(nf);
+            free(dense);
+            free(host);
+            return cudaErrorMemoryAllocation;
+        }
+        uint32_t* h_klo = host;
+        uint32_t* h_khi = h_klo + 128;
+        uint32_t* h_vals = h_khi + 64;
+        uint16_t* h_dense16 = reinterpret_cast<uint16_t*>(h_vals + EVAL_DENSE_SIZE);
+        uint8_t* h_disp = reinterpret_cast<uint8_t*>(h_dense16 + EVAL_DENSE_SIZE);
+        const bool built = eval_nf_table_fill(nf, true) == 49205u && eval_fast_table_fill(nf, h_disp, dense);
+        free(nf);
+        uint32_t nvals = 0;
+        if (built) {  // classes: the distinct words of the value table, ascending (the empty slots' 0 is class 0)
+            uint32_t* sorted = dense + EVAL_DENSE_SIZE;
+            memcpy(sorted, dense, (size_t)EVAL_DENSE_SIZE * 4);
+            std::sort(sorted, sorted + EVAL_DENSE_SIZE);
+            nvals = (uint32_t)(std::unique(sorted, sorted + EVAL_DENSE_SIZE) - sorted);
+            memcpy(h_vals, sorted, (size_t)nvals * 4);
+            for (uint32_t i = 0; i < EVAL_DENSE_SIZE; ++i) h_dense16[i] = (uint16_t)(std::lower_bound(sorted, sorted + nvals, dense[i]) - sorted);
+        }
+        free(dense);
+        if (!built || nvals > 8192u) {  // 8192 classes = 32 KB is what the kernel's shared-memory budget allows (there are ~3,500)
+            free(host);
+            return cudaErrorUnknown;
+        }
+        for (uint32_t x = 0; x < 128u; ++x) h_klo[x] = fast_klo_entry(x);
+        for (uint32_t x = 0; x < 64u; ++x) h_khi[x] = fast_khi_entry(x);
+        uint32_t* dptr = nullptr;
+        e = cudaMalloc(&dptr, words * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(dptr, host, words * 4, cudaMemcpyHostToDevice);
+        free(host);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(eval_masks_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_fast_smem(nvals));
+        if (e != cudaSuccess) {
+            cudaFree(dptr);
+            return e;
+        }
+        uint32_t* d_vals = dptr + 128 + 64;
+        const uint16_t* d_dense16 = reinterpret_cast<const uint16_t*>(d_vals + EVAL_DENSE_SIZE);
+        tabs[dev] = EvalFastTables{dptr, dptr + 128, reinterpret_cast<const uint8_t*>(d_dense16 + EVAL_DENSE_SIZE), d_dense16, d_vals, nvals};
+        ready[dev] = true;
+    }
+    *out = tabs[dev];
+    return cudaSuccess;
+}
+
 int pkb_eval_masks(const uint64_t* masks, uint64_t n, uint32_t* out, void* stream)
 {
     if (n == 0) return 0;
     if (!out || !masks) return fail("pkb_eval_masks: null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const bool use_table = getenv("PKB_EVAL_IMPL") && !strcmp(getenv("PKB_EVAL_IMPL"), "table");
+    static const bool use_hash3 = getenv("PKB_EVAL_IMPL") && !strcmp(getenv("PKB_EVAL_IMPL"), "hash3");  // round 2's first kernel, for comparison
     const uint64_t want = (n / 2 + EVAL_THREADS - 1) / EVAL_THREADS;
     if (use_table) {  // the rank-set-table evaluator (comparison): six 256-thread blocks per SM, the 32 KB table each
         PKB_CUDA(ensure_eval_table(s));
         const unsigned grid = (unsigned)(want < 148ull * 6 ? (want ? want : 1) : 148ull * 6);
         eval_masks_kernel<<<grid, EVAL_THREADS, 0, s>>>(masks, n, out);
-    } else {
+    } else if (n >= EVAL_FAST_MIN_HANDS && !use_hash3 && (reinterpret_cast<uintptr_t>(masks) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+        // the streaming evaluator: one block per SM, every table in shared memory; ring entries are 32-bit hand indices
+        EvalFastTables t;
+        PKB_CUDA(ensure_eval_fast_tables(&t));
+        int dev = 0, sms = 0;
+        PKB_CUDA(cudaGetDevice(&dev));
+        PKB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const uint64_t chunk = 1ull << 31;
+        for (uint64_t lo = 0; lo < n; lo += chunk) {
+            const uint64_t cnt = n - lo < chunk ? n - lo : chunk;
+            eval_masks_fast_kernel<<<(unsigned)sms, EVAL_FAST_THREADS, eval_fast_smem(t.nvals), s>>>(masks + lo, cnt, out + lo, t);
+        }
+    } else {  // small batches and unaligned arrays
         EvalHashTables t;
         PKB_CUDA(ensure_eval_hash_tables(&t));
         const unsigned grid = (unsigned)(want < 148ull * PKB_EVAL_MIN_BLOCKS ? (want ? want : 1) : 148ull * PKB_EVAL_MIN_BLOCKS);

@@ -82,6 +82,50 @@ long long hc_eval_hash3_mismatches(uint64_t count)
     }
     return bad;
 }
+// the streaming form (eval7_fast): every seven-card hand is either marked rare or its table value equals the bitmask
+// evaluator; returns mismatches, *rare_count = hands marked rare; -1 / -2 as above.  Masks with other card counts
+// (k != 7, first `other` masks of each k in 0..8) must all be marked rare: -3 if one is not.
+long long hc_eval_fast_mismatches(uint64_t count, uint64_t* rare_count, uint64_t other)
+{
+    static uint32_t* nf = nullptr;
+    static uint32_t klo[128], khi[64];
+    static uint8_t* disp = nullptr;
+    static uint32_t* dense = nullptr;
+    if (!nf) {
+        nf = new uint32_t[pkb::EVAL_NF_SIZE];
+        if (pkb::eval_nf_table_fill(nf, true) != 49205u) return -1;
+        disp = new uint8_t[pkb::EVAL_FAST_BUCKETS];
+        dense = new uint32_t[pkb::EVAL_DENSE_SIZE];
+        if (!pkb::eval_fast_table_fill(nf, disp, dense)) return -2;
+        for (uint32_t x = 0; x < 128u; ++x) klo[x] = pkb::fast_klo_entry(x);
+        for (uint32_t x = 0; x < 64u; ++x) khi[x] = pkb::fast_khi_entry(x);
+    }
+    uint64_t m = (1ull << 7) - 1, rares = 0;
+    long long bad = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        uint32_t rare = 0;
+        const uint32_t v = pkb::eval7_fast(m, klo, khi, 1, 0, disp, dense, &rare);
+        if (rare) ++rares;
+        else bad += v != pkb::eval_mask52(m);
+        const uint64_t c = m & -m, r = m + c;
+        m = (((r ^ m) >> 2) / c) | r;
+    }
+    for (int k = 0; k <= 8; ++k) {
+        if (k == 7) continue;
+        uint64_t mk = (1ull << k) - 1;
+        for (uint64_t i = 0; i < other; ++i) {
+            uint32_t rare = 0;
+            (void)pkb::eval7_fast(mk, klo, khi, 1, 0, disp, dense, &rare);
+            if (!rare) return -3;
+            if (k == 0) break;
+            const uint64_t c = mk & -mk, r = mk + c;
+            mk = ((((r ^ mk) >> 2) / c) | r) & ((1ull << 52) - 1);
+            if (!mk || pkb::popc64(mk) != k) break;
+        }
+    }
+    if (rare_count) *rare_count = rares;
+    return bad;
+}
 uint32_t hc_eval_cards(const uint8_t* c, int n) { return pkb::eval_cards(c, n); }
 uint32_t hc_eval_cards_literal(const uint8_t* c, int n) { return pkb::eval_cards_literal(c, n); }
 
@@ -94,6 +138,17 @@ static uint64_t next_same_popcount(uint64_t v)
 {
     uint64_t c = v & -v, r = v + c;
     return (((r ^ v) >> 2) / c) | r;
+}
+
+// `count` masks of k cards in increasing order starting at `start` (0: the lowest, (1 << k) - 1); returns the next one
+uint64_t hc_enumerate_masks(int k, uint64_t start, uint64_t count, uint64_t* out)
+{
+    uint64_t m = start ? start : (1ull << k) - 1;
+    for (uint64_t i = 0; i < count; ++i) {
+        out[i] = m;
+        m = next_same_popcount(m);
+    }
+    return m;
 }
 
 // all C(52,k) masks in increasing order starting from the lowest; hist/sums as pkb_eval_exhaustive

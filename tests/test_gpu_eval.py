@@ -18,6 +18,12 @@ def torch_cuda():
     return torch
 
 
+@pytest.fixture(scope="module")
+def hc():
+    from tests.hostcheck import load
+    return load()
+
+
 def test_native_library_loaded(torch_cuda):
     from pokerl_b200 import _native as nat
     assert nat.require_cuda() >= 1
@@ -108,6 +114,58 @@ def test_random_hands_and_mask_eval(torch_cuda, ora):
     assert np.array_equal(got, ora.eval_masks_batch(m))
     again = random_hands(0, 1 << 20)
     assert torch.equal(masks, again)  # counter-based: same seed, same hands
+
+
+def test_mask_eval_on_every_seven_card_hand(torch_cuda, hc):
+    """The streaming batch evaluator (eval_masks_fast_kernel: shared-memory perfect hash, rare hands queued per warp)
+    on ALL C(52,7) masks, in the enumeration order of the exhaustive kernel: element-wise equal to that kernel's
+    output (which test_exhaustive_all_hands_bit_exact pins to the oracle and the golden checksums)."""
+    import ctypes as C
+    torch = torch_cuda
+    from pokerl_b200.judger import eval_exhaustive, eval_masks_batch
+    n = comb(52, 7)
+    want = torch.empty(n, dtype=torch.int32, device="cuda")
+    eval_exhaustive(7, out=want)
+    hc.hc_enumerate_masks.restype = C.c_uint64
+    hc.hc_enumerate_masks.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+    step, start = 1 << 25, 0
+    buf = np.empty(step, dtype=np.uint64)
+    for lo in range(0, n, step):
+        cnt = min(step, n - lo)
+        start = hc.hc_enumerate_masks(7, start, cnt, buf.ctypes.data)
+        got = eval_masks_batch(torch.from_numpy(buf[:cnt].view(np.int64)).cuda())
+        assert torch.equal(got, want[lo:lo + cnt]), lo
+
+
+def test_mask_eval_mixed_sizes_ragged_and_unaligned(torch_cuda, ora):
+    """Masks of 0..7 cards mixed in one batch (everything but seven cards takes the queue of rare hands), batch sizes
+    around the streaming kernel's trip size and threshold, and arrays that start at odd elements (the unaligned path)."""
+    torch = torch_cuda
+    from pokerl_b200 import _native as nat
+    rng = np.random.default_rng(5)
+    n = (1 << 18) + 77
+    k = rng.integers(0, 8, size=n)
+    k[: n // 2] = 7
+    rng.shuffle(k)
+    order = np.argsort(rng.random((n, 52)), axis=1)
+    bits = (np.arange(52)[None, :] < k[:, None])
+    ids = np.where(bits, order, 63)
+    m = np.zeros(n, dtype=np.uint64)
+    for j in range(7):
+        sel = ids[:, j] < 52
+        m[sel] |= np.uint64(1) << ids[sel, j].astype(np.uint64)
+    assert (np.bitwise_count(m) == k).all()
+    want = ora.eval_masks_batch(m)
+    dm = torch.from_numpy(m.view(np.int64)).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    for lo, cnt in ((0, n), (0, 1 << 17), (0, (1 << 17) + 127), (0, (1 << 17) - 1), (1, (1 << 17) + 5), (3, n - 3), (2, 1 << 17), (0, 1000)):
+        out = torch.full((cnt + 3,), -1, dtype=torch.int32, device="cuda")
+        for off in (0, 1):
+            masks = dm[lo:lo + cnt]
+            nat.check(nat.lib().pkb_eval_masks(masks.data_ptr(), cnt, out[off:].data_ptr(), stream))
+            got = out[off:off + cnt].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, want[lo:lo + cnt]), (lo, cnt, off)
+            assert (out[off + cnt:] == -1).all()
 
 
 def test_empty_and_ragged_inputs(torch_cuda):

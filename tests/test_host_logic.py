@@ -77,6 +77,19 @@ def test_perfect_hash_evaluator_equals_bitmask_evaluator(hc):
     assert hc.hc_eval_hash3_mismatches(133_784_560) == 0
 
 
+def test_streaming_hash_evaluator_equals_bitmask_evaluator_or_says_rare(hc):
+    """The streaming form of the perfect hash (pkb_eval.cuh eval7_fast: key tables that also count cards per suit,
+    16-bit first level per 1024 key sums, rank-wheel mark in the value table): on ALL C(52,7) hands it either marks the
+    hand rare (a suit with five cards, or with 2,3,4,5 and no six: the batch kernel ranks those with the select evaluator) or returns
+    exactly the bitmask evaluator's value; masks with any other number of cards are always marked rare."""
+    hc.hc_eval_fast_mismatches.restype = C.c_longlong
+    hc.hc_eval_fast_mismatches.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64]
+    rare = C.c_uint64(0)
+    assert hc.hc_eval_fast_mismatches(133_784_560, C.byref(rare), 200_000) == 0
+    # flushes (incl. straight flushes): 4,089,228 + ... ; what matters here: rare hands are a small minority
+    assert 0 < rare.value < 0.035 * 133_784_560, rare.value
+
+
 def test_all_at_once_deal_equals_sequential_dealer(hc):
     """deal_ids (interleaved Philox blocks + sorted draw chain, P <= 4) deals exactly the cards of the sequential Dealer."""
     rng = np.random.default_rng(3)
