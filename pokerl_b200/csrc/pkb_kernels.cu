@@ -1035,11 +1035,21 @@ eval_masks_fast_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t*
     const uint64_t trips = n / (32 * HPT), wstride = (uint64_t)gridDim.x * WARPS;
     uint32_t head = 0, tail = 0;
     uint32_t* q = s_queue + w * QSIZE;
-    for (uint64_t trip = (uint64_t)blockIdx.x * WARPS + w; trip < trips; trip += wstride) {
+    const uint64_t first = (uint64_t)blockIdx.x * WARPS + w;
+    ulonglong2 nxt[HPT / 2];
+    if (first < trips) {
+#pragma unroll
+        for (int j = 0; j < HPT / 2; ++j) nxt[j] = reinterpret_cast<const ulonglong2*>(masks)[first * (16 * HPT) + lane + 32 * j];
+    }
+    for (uint64_t trip = first; trip < trips; trip += wstride) {
         const uint64_t pair0 = trip * (16 * HPT) + lane;  // this lane's pairs of hands: pair0 + 32 j
         ulonglong2 m[HPT / 2];
 #pragma unroll
-        for (int j = 0; j < HPT / 2; ++j) m[j] = reinterpret_cast<const ulonglong2*>(masks)[pair0 + 32 * j];
+        for (int j = 0; j < HPT / 2; ++j) m[j] = nxt[j];
+        if (trip + wstride < trips) {  // the next trip's masks are in flight while this one is ranked (+4 %: 335 -> 348 G evals/s)
+#pragma unroll
+            for (int j = 0; j < HPT / 2; ++j) nxt[j] = reinterpret_cast<const ulonglong2*>(masks)[pair0 + wstride * (16 * HPT) + 32 * j];
+        }
         uint32_t r[HPT], rare[HPT];
 #pragma unroll
         for (int j = 0; j < HPT / 2; ++j) {
