@@ -12,18 +12,20 @@ import torch  # noqa: E402
 from pokerl_b200 import GameBatch  # noqa: E402
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-g = GameBatch(1 << 20, P, 100, 2, 1, seed=0, auto_reset=True)
+start = 100 if P != 9 else [20 * (i + 1) for i in range(9)]   # nine players: the stacks and action mix of BASELINE configs[3]
+weights = None if P != 9 else [10, 30, 30, 5, 5, 5, 45]
+g = GameBatch(1 << 20, P, start, 2, 1, seed=0, auto_reset=True)
 g.reset()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for t in range(20):
-    g.step_random(t)
+    g.step_random(t, weights)
 torch.cuda.synchronize()
 L = C.CDLL(os.environ["PKB_LIB"])
 CHAIN = int(os.environ.get("PKB_TIMING_CHAIN", "1"))  # > 1: that many back-to-back launches (pipelined); the table shows the last
 for rep in range(3):
     flush.zero_()
     for k in range(CHAIN):
-        g.step_random(99 + rep * CHAIN + k)
+        g.step_random(99 + rep * CHAIN + k, weights)
     torch.cuda.synchronize()
     buf = (C.c_ulonglong * (4096 * 16))()
     L.pkb_debug_warps(buf)
