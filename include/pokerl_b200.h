@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PKB_ABI_VERSION 3
+#define PKB_ABI_VERSION 4
 #define PKB_MAX_PLAYERS 10
 #define PKB_NUM_MOVES 7
 
@@ -71,16 +71,20 @@ typedef struct pkb_config {
 } pkb_config;
 
 /* Device pointers into the handle's state, for zero-copy wrapping (torch / cupy / raw CUDA).
- * f64 planes are [num_players][stride] (seat-major, env fastest); the rest are [stride]. */
+ * credits / bets / pending_bets are [num_players][stride] (seat-major, env fastest), payoffs is [stride][payoff_pitch],
+ * the rest are [stride]. */
 typedef struct pkb_state_view {
     uint64_t num_envs;
     uint64_t stride;          /* elements between consecutive seats (num_envs rounded up to the tile) */
     int32_t num_players;
-    int32_t reserved;
+    int32_t payoff_pitch;     /* doubles per env in `payoffs`: num_players rounded up to a multiple of 4 */
     double *credits;          /* Game.credits                 game.py:260 */
     double *bets;             /* Game.bets                    game.py:261 */
     double *pending_bets;     /* Game.pending_bets            game.py:262 */
-    double *payoffs;          /* Game.payoffs                 game.py:264 */
+    double *payoffs;          /* Game.payoffs                 game.py:264 -- ENV-major, unlike the other planes:
+                               * payoffs[env * payoff_pitch + seat]; the padding doubles of a record are 0.0.  (A step
+                               * writes payoffs only where a hand ended; whole 32-byte records keep those scattered
+                               * writes from pulling the rest of each sector out of HBM.) */
     double *minimum_raise_value; /* Game.minimum_raise_value  game.py:263 */
     uint64_t *seat_masks;     /* Game.player_states game.py:259 as seat bit masks, one word per env [stride]:
                                * ACTIVE | CALLED<<16 | ALL_IN<<32 | BROKEN<<48, bit p of a field = seat p (FOLDED: in

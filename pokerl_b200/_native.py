@@ -8,7 +8,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_PLAYERS = 10
 NUM_MOVES = 7
 
@@ -40,7 +40,7 @@ class PkbStateView(C.Structure):
         ("num_envs", C.c_uint64),
         ("stride", C.c_uint64),
         ("num_players", C.c_int32),
-        ("reserved", C.c_int32),
+        ("payoff_pitch", C.c_int32),
         ("credits", C.c_void_p),
         ("bets", C.c_void_p),
         ("pending_bets", C.c_void_p),

@@ -101,7 +101,8 @@ class GameBatch:
         self.credits = wrap(sv.credits, (P, S), "<f8")[:, :N]
         self.bets = wrap(sv.bets, (P, S), "<f8")[:, :N]
         self.pending_bets = wrap(sv.pending_bets, (P, S), "<f8")[:, :N]
-        self.payoffs = wrap(sv.payoffs, (P, S), "<f8")[:, :N]
+        # Game.payoffs is stored env-major (one zero-padded record of payoff_pitch doubles per env): a strided [P, N] view
+        self.payoffs = wrap(sv.payoffs, (S, int(sv.payoff_pitch)), "<f8")[:N, :P].T
         self.minimum_raise_value = wrap(sv.minimum_raise_value, (S,), "<f8")[:N]
         # player_states live on the device as four 16-bit seat masks per env (ACTIVE | CALLED<<16 | ALL_IN<<32 | BROKEN<<48)
         self.seat_masks = wrap(sv.seat_masks, (S,), "<i8")[:N]
@@ -322,7 +323,7 @@ class GameBatch:
         meta = self._meta.cpu().numpy().astype(np.int64)
         return dict(
             credits=self.credits.cpu().numpy(), bets=self.bets.cpu().numpy(), pending=self.pending_bets.cpu().numpy(),
-            payoffs=self.payoffs.cpu().numpy(), states=self.player_states.cpu().numpy(),
+            payoffs=self.payoffs.contiguous().cpu().numpy(), states=self.player_states.cpu().numpy(),
             minraise=self.minimum_raise_value.cpu().numpy(), turn=(meta & 7).astype(np.int32),
             dealer=((meta >> 3) & 31).astype(np.int32), sb=((meta >> 8) & 31).astype(np.int32),
             bb=((meta >> 13) & 31).astype(np.int32), active=((meta >> 18) & 31).astype(np.int32),

@@ -25,6 +25,22 @@ constexpr int NEXT_TURN_CAP = 64;
 constexpr int MAX_PLAYERS = 10;
 
 // per-handle constants, passed by value to every kernel (Game(**config), game.py:246-251)
+// Game.payoffs (game.py:264) is stored env-major: one record of payoff_pitch(P) doubles per env, P payoffs and zero padding
+// up to a multiple of four.  Payoffs are written only by the steps that end a hand (a third of the heads-up steps), from
+// scattered envs: with seat-major planes every such env touched one 32-byte sector per seat and left most of each sector
+// unwritten -- the L2 had to fetch the rest from HBM before it could write the sector back (27 MB of the 186 MB a heads-up
+// launch moved, and 4.9 % of its time, measured with the stores compiled out).  A record is whole sectors, written by
+// 256-bit stores: nothing is fetched, and one store per env replaces one per seat.
+PKB_HD constexpr int payoff_pitch(int P) { return (P + 3) & ~3; }
+PKB_D void store_f64x4(double* p, double a, double b, double c, double d)  // p 32-byte aligned
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+
 struct GameConst {
     double start_credits[MAX_PLAYERS];
     double big_blind, small_blind;
@@ -612,17 +628,22 @@ PKB_D void showdown_settle(V& v, size_t s, const Seats& x, int npw)
 // return value (game.py:565 / 609-611 or game.py:619).  `pay_out` receives the hand's final payoffs.
 // With `auto_reset`, a finished game is reset right here (Game.reset, game.py:397-412).  Returns true if it reset.
 template <int P, class V>
-PKB_D bool end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* payoffs_out, size_t out_ld, size_t out_idx,
-                           double (&pay_out)[P], const GameConst& gc)
+PKB_D bool end_hand_finish(V& v, size_t s, Seats& x, Meta& m, Ctl& c, double* pay_record, double (&pay_out)[P], const GameConst& gc)
 {
     const size_t ld = v.ld();
+    double rec[payoff_pitch(P)];
+#pragma unroll
+    for (int p = 0; p < payoff_pitch(P); ++p) rec[p] = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const double pay = v.pd[p * ld + s] - v.bt[p * ld + s];  // :531
-        pay_out[p] = pay;
-        payoffs_out[p * out_ld + out_idx] = pay;
+        pay_out[p] = rec[p] = pay;
         if (v.cr[p * ld + s] <= 0.0) set_state(x, p, ST_BROKEN);  // :536
     }
+#ifndef PKB_PROBE_NO_PAYOFF_STORE  // timing probe only (profiles/): what the payoff stores cost
+#pragma unroll
+    for (int q = 0; q < payoff_pitch(P); q += 4) store_f64x4(pay_record + q, rec[q], rec[q + 1], rec[q + 2], rec[q + 3]);
+#endif
     // :539 setup_hand runs even when the game is over -- and it can bring BROKEN seats with a negative
     // stack back as ALL_IN, so game_over is read after it, as the callers do
     // (:565, :619).

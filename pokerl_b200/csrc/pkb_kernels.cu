@@ -617,13 +617,13 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                         // game.py:473 `assert num_potential_winners > 0` would fire: payoffs were zeroed at :468; the step
                         // reports hand-over (and round-over when end_hand was entered from next_turn) plus PKB_F_POISONED
 #pragma unroll
-                        for (int p = 0; p < P; ++p) d.payoffs[p * d.stride + env] = 0.0;
+                        for (int q = 0; q < payoff_pitch(P); q += 4) store_f64x4(d.payoffs + env * payoff_pitch(P) + q, 0.0, 0.0, 0.0, 0.0);
                         c.done = c.cont ? (int)((game_over<P>(x) ? F_GAME_OVER : 0u) | F_HAND_OVER | F_ROUND_OVER) : (int)F_HAND_OVER;
                         c.pc = PC_DONE;
                     } else {
                         c.pc = PC_DONE;
                         double pay[P];
-                        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs, d.stride, env, pay, a.gc)) ep[s] += 1;
+                        if (end_hand_finish<P>(v, s, x, m, c, d.payoffs + env * payoff_pitch(P), pay, a.gc)) ep[s] += 1;
 #pragma unroll
                         for (int p = 0; p < P; ++p) tl.pay[p] += pay[p];
                         if (c.pc == PC_END_HAND) {  // another hand ends inside this step: its head now, the rest next round
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                         out_v[s] = (uint8_t)m.vm;
                         ec = EC_RESET_LOOP | (m.act != 0 && !cap_hit ? EC_PENDING : 0u);
                     }
-                    if ((ec & EC_WRITE_REWARD) && a.reward) a.reward[env] = (ec & EC_REWARD) ? d.payoffs[env] : 0.0;  // payoffs[agent]: seat 0's row
+                    if ((ec & EC_WRITE_REWARD) && a.reward) a.reward[env] = (ec & EC_REWARD) ? d.payoffs[env * payoff_pitch(P)] : 0.0;  // payoffs[agent]: seat 0 leads the env's record
                     if (!(ec & EC_PENDING) && !a.env_reset && a.env_done) a.env_done[env] = (uint8_t)env_out_byte(ec);  // step() returns
                     act_row[s] = (uint8_t)(ec & 255u);
                     pending = (ec & EC_PENDING) != 0;
@@ -1429,7 +1429,7 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
     const int P = cfg->num_players;
     const uint64_t n = cfg->num_envs, stride = (n + STRIDE_ALIGN - 1) / STRIDE_ALIGN * STRIDE_ALIGN;
     // arena: 8-byte planes (f64 money, seat masks) | u32 planes | stats
-    const size_t n_w64 = (size_t)(4 * P + 2) * stride, n_u32 = (size_t)3 * stride;
+    const size_t n_w64 = (size_t)(3 * P + 2 + payoff_pitch(P)) * stride, n_u32 = (size_t)3 * stride;  // payoffs: one padded record per env
     const size_t off_u32 = n_w64 * 8, off_stats = (off_u32 + n_u32 * 4 + 255) / 256 * 256;
     const size_t off_seq = (off_stats + STAT_COUNT * 8 + MAX_PLAYERS * 8 + NUM_MOVES * 4 + 4 + 255) / 256 * 256;
     const size_t n_epoch = stride / 32;  // one word per tile; tiles hold at least 32 envs
@@ -1718,7 +1718,7 @@ int pkb_state(pkb_env* h, pkb_state_view* out)
     out->num_envs = h->d.n;
     out->stride = h->d.stride;
     out->num_players = h->cfg.num_players;
-    out->reserved = 0;
+    out->payoff_pitch = payoff_pitch(h->cfg.num_players);
     out->credits = h->d.cr;
     out->bets = h->d.bt;
     out->pending_bets = h->d.pd;
