@@ -10,6 +10,8 @@ python profiles/chain_bench.py --players 9 --steps 100 > gpurun_out/r02/chain_p9
 python profiles/chain_bench.py --players 4 --steps 100 > gpurun_out/r02/chain_p4.log 2>&1
 python profiles/ramp_probe.py > gpurun_out/r02/ramp_probe.log 2>&1
 python profiles/eval_bench.py > gpurun_out/r02/eval_bench.log 2>&1
+PKB_EVAL_IMPL=hash3 python profiles/eval_bench.py >> gpurun_out/r02/eval_bench.log 2>&1
+python profiles/exhaustive_bench.py > gpurun_out/r02/exhaustive_bench.log 2>&1
 # launch list of the bench command (serialised, cold cache: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02/ncu_launches.log 2>&1
@@ -20,5 +22,5 @@ PKB_RANGE_LAUNCHES=12 PKB_RANGE_PLAYERS=9 ncu --replay-mode range --cache-contro
 # full-set captures of one launch each (L2 flushed before the step by prof_step.py)
 ncu --set full --clock-control none --import-source on -k regex:step_warp -s 36 -c 1 -f -o gpurun_out/r02/step_p2 python profiles/prof_step.py --steps 40 > gpurun_out/r02/ncu_full_p2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:step_warp -s 36 -c 1 -f -o gpurun_out/r02/step_p9 python profiles/prof_step.py --players 9 --steps 40 > gpurun_out/r02/ncu_full_p9.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:eval_masks_hash -s 1 -c 1 -f -o gpurun_out/r02/eval_hash python profiles/prof_step.py --steps 2 --eval > gpurun_out/r02/ncu_full_eval.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:eval_masks_fast -s 2 -c 1 -f -o gpurun_out/r02/eval_fast python profiles/eval_prof.py > gpurun_out/r02/ncu_full_eval.log 2>&1
 ls -la gpurun_out/r02
