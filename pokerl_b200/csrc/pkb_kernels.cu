@@ -448,7 +448,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         }
         // The previous tile's store was issued just before this tile's load: waiting for it to be performed and releasing
         // its epoch (a GPU-scope fence) costs about what the load takes, and the warp has nothing else to do until then.
+#ifndef PKB_PUBLISH_AFTER_A
         if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
+#endif
         mbar_wait(bar, it & 1u);
 #ifdef PKB_TIMING
         wt_lw[it < 2 ? it : 2] += (unsigned long long)(clock64() - wt_last);
@@ -549,6 +551,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         // the previous tile's store has had pass A's time to finish: publish it without waiting
         // one look at the next tile's epoch while passes C and D run: the acquire's round trip is off the load's path
         if (lane == 0) handed_over = next < a.num_tiles && ld_acquire_u32(&d.epoch[next]) == launch;
+#ifdef PKB_PUBLISH_AFTER_A
+        if (lane == 0 && stored != 0xffffffffu) { epoch_publish(&d.epoch[stored], launch + 1u); stored = 0xffffffffu; }
+#endif
 
         // Passes C and D repeat while hands keep ending inside this step (all-in blinds: a slot whose next hand
         // cannot be acted on either); such slots go round again through the SAME code, side by side.
