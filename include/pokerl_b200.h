@@ -151,7 +151,7 @@ int pkb_step_random(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int3
 /* ---- PokerGameEnv: envs/game_env.py ---------------------------------------------------------------------------
  * The reference's RL environment seats the learning agent in seat 0 and lets callables play the other seats.  With the
  * device-side random agent in those seats (weights as for pkb_step_random; NULL = RandomAgent, agents/random.py:16-17)
- * both of its entry points are ONE launch each: the kernel keeps stepping an env -- one sampled opponent move per round,
+ * both of its entry points are ONE call each: the kernel keeps stepping an env -- one sampled opponent move per round,
  * inside the tile -- until the reference's loops would return.  The j-th opponent move of an env inside a call draws
  * with sampler step index round_base + j - 1 (j = 1, 2, ...; at most PKB_ENV_ROUND_CAP per call, then the env is given
  * up as poisoned), so callers advance round_base by PKB_ENV_ROUND_CAP from call to call.
@@ -168,6 +168,12 @@ int pkb_env_step(pkb_env *h, const int32_t *actions, uint32_t round_base, const 
                  uint8_t *done, uint8_t *valid, void *stream);
 int pkb_env_reset(pkb_env *h, const uint8_t *env_mask, uint32_t round_base, const uint32_t *weights, uint8_t *valid,
                   void *stream);
+/* pkb_env_step on large handles runs in PHASES: the launch over the handle's planes plays six opponent rounds, the envs
+ * whose opponents are still playing after that (an agent that has folded or gone broke; envs/game_env.py:41-52) are
+ * packed into a scratch arena and stepped there by follow-up launches (12, 32, then all remaining rounds).  Results do
+ * not depend on it.  min_envs: handles with at least this many envs use phases (default 16384; 0: always; < 0: never).
+ * The scratch arena (the size of the handle's state) is allocated by the first phased call. */
+int pkb_set_env_phases(pkb_env *h, int64_t min_envs);
 /* Sampler alone (K5): actions for the CURRENT state, without stepping. */
 int pkb_sample_actions(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int32_t *actions_out, void *stream);
 /* Game.get_valid_actions(player), game.py:339-383.  player < 0: each env's active player. */

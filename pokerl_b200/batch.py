@@ -164,6 +164,11 @@ class GameBatch:
         """Whether consecutive step launches may overlap (default on; results are identical either way)."""
         nat.check(nat.lib().pkb_set_pipelining(self._h.ptr, int(bool(enabled))))
 
+    def set_env_phases(self, min_envs: int):
+        """PokerGameEnv.step in phases (stragglers packed into a scratch arena) for handles of at least min_envs envs
+        (default 16384; 0: always; negative: never).  Results are identical either way."""
+        nat.check(nat.lib().pkb_set_env_phases(self._h.ptr, int(min_envs)))
+
     def reset(self, env_mask=None):
         """Game.reset() on every env, or on those where env_mask (uint8/bool [N]) is nonzero."""
         if env_mask is not None:

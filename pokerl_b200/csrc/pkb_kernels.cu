@@ -70,6 +70,17 @@ struct StepArgs {
     const uint8_t* env_mask;    // reset: envs to reset (null: all)
     double* reward;             // step outputs, one per env
     uint8_t* env_done;          //   bit 0 done, bit 1 hand_over, bit 5 not stepped (PKB_ACTION_SKIP), bit 6 rejected, bit 7 poisoned
+    // PokerGameEnv.step in phases (env_step_phases): a launch plays at most env_round_cap opponent rounds and hands the envs
+    // whose loop has not returned to the next phase, which runs them packed densely in a scratch arena
+    uint32_t env_round_cap;      // opponent rounds this launch may play (0: no limit but ENV_ROUND_CAP)
+    uint32_t env_round_offset;   // continue mode: opponent moves every env of this launch has already made in this call
+    uint32_t no_epoch;           // scratch arena: plain stream order, no tile hand-over between launches
+    const uint32_t* env_ids;     // continue mode: slot i of this launch is env env_ids[i] of the handle (null: identity)
+    const uint32_t* n_dev;       // continue mode: the number of envs of this launch, on the device
+    const uint8_t* env_ctl_in;   // continue mode: the control byte of every slot as the previous phase left it
+    uint32_t* strag_count;       // out (null: none): envs still pending when the cap is reached -- how many,
+    uint32_t* strag_ids;         //   which (indices into the handle's planes)
+    uint8_t* strag_ctl;          //   and their control bytes
 };
 
 #ifndef PKB_STRIDE_ALIGN
@@ -337,6 +348,9 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem[];
     const DevState& d = a.d;
+    // the envs of this launch: the handle's, or (env mode, continue phase) as many as the previous phase left pending
+    const size_t n_envs = ENV && a.n_dev ? (size_t)*a.n_dev : d.n;
+    const uint32_t num_tiles = ENV && a.n_dev ? (uint32_t)((n_envs + T - 1) / T) : a.num_tiles;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* buf = smem + L::HEADER + (size_t)warp * L::WARP_BYTES;
     const uint32_t bar = smem_u32(smem) + 8u * (uint32_t)warp, buf_s = smem_u32(buf);
@@ -394,22 +408,22 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     uint32_t tile = blockIdx.x * L::WARPS + warp;
     uint32_t stored = 0xffffffffu;  // lane 0: the tile whose store is in flight and whose epoch is still to be published
     bool handed_over = false;       // lane 0: the acquire of the coming tile's epoch has already succeeded (polled a pass early)
-    for (uint32_t it = 0; tile < a.num_tiles; ++it) {
+    for (uint32_t it = 0; tile < num_tiles; ++it) {
         const size_t base = (size_t)tile * T;
         if (lane == 0) {  // two TMA box copies bring the tile in, once the previous launch has stored it
-            if (!handed_over) epoch_wait(&d.epoch[tile], launch);
+            if (!handed_over && !a.no_epoch) epoch_wait(&d.epoch[tile], launch);
             fence_async_global();  // the tile was written through the async proxy and is about to be read through it
             mbar_arrive_expect_tx(bar, (uint32_t)L::BUF_BYTES);
             tma_load_2d(buf_s + (uint32_t)L::OFF_CR, &a.maps.w64, (int)base, 0, bar);
             tma_load_2d(buf_s + (uint32_t)L::OFF_META, &a.maps.u32, (int)base, 0, bar);
         }
         const uint32_t next = tile + warps_total;
-        if (!SAMPLE) {  // the caller's actions, as bytes (254: out of range, 255: skip), fetched while the tile is in flight
+        if (!SAMPLE && !(ENV && a.env_ids)) {  // the caller's actions, as bytes (254: out of range, 255: skip), fetched while the tile is in flight
 #pragma unroll
             for (int k = 0; k < T / 32; ++k) {
                 const size_t env = base + (size_t)(lane + 32 * k);
                 uint32_t b = 254u;
-                if (env < d.n) {
+                if (env < n_envs) {
                     if (ENV && a.env_reset) {  // PokerGameEnv.reset: the byte says whether this env takes part
                         b = (!a.env_mask || a.env_mask[env]) ? 1u : 0u;
                     } else if (a.actions) {
@@ -448,9 +462,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         }
         // The previous tile's store was issued just before this tile's load: waiting for it to be performed and releasing
         // its epoch (a GPU-scope fence) costs about what the load takes, and the warp has nothing else to do until then.
-#ifndef PKB_PUBLISH_AFTER_A
-        if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
-#endif
+        if (lane == 0 && stored != 0xffffffffu && !a.no_epoch) epoch_publish(&d.epoch[stored], launch + 1u);
         mbar_wait(bar, it & 1u);
 #ifdef PKB_TIMING
         wt_lw[it < 2 ? it : 2] += (unsigned long long)(clock64() - wt_last);
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             for (int s = lane; s < T; s += 32) {
                 bool pending = false;
                 uint32_t vm_now = 0;
-                if (base + s < d.n) {
+                if (base + s < n_envs) {
                     Meta m = unpack_meta(v.meta[s]);
                     if (act_row[s]) {  // Game.reset (game_env.py:23)
                         Seats x{0, 0, 0, 0};
@@ -489,11 +501,24 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             }
             env_round = 1;
             __syncwarp();
+        } else if (ENV && a.env_ids) {  // continue phase: every slot is an env whose loop had not returned when the last phase stopped
+            for (int s = lane; s < T; s += 32) {
+                const bool have = base + s < n_envs;
+                if (have) {
+                    act_row[s] = a.env_ctl_in[base + s];
+                    out_f[s] = 0;
+                    out_v[s] = (uint8_t)unpack_meta(v.meta[s]).vm;
+                    pend[s] = (uint8_t)s;
+                }
+            }
+            n_pend = (uint32_t)(n_envs - base < (size_t)T ? n_envs - base : (size_t)T);
+            env_round = 1;
+            __syncwarp();
         }
-        for (bool env_more = !(ENV && a.env_reset) || n_pend != 0; env_more;) {
+        for (bool env_more = !(ENV && (a.env_reset || a.env_ids)) || n_pend != 0; env_more;) {
         // ---- pass A: every slot
         uint32_t n_e = 0, n_s = 0;  // list lengths (warp-uniform)
-        const uint32_t n_live = d.n - base < (size_t)T ? (uint32_t)(d.n - base) : (uint32_t)T;  // slots of this tile that are envs
+        const uint32_t n_live = n_envs - base < (size_t)T ? (uint32_t)(n_envs - base) : (uint32_t)T;  // slots of this tile that are envs
         const uint32_t n_visit = ENV && env_round ? n_pend : (uint32_t)T;
         PKB_UNROLL(PKB_WT_UNROLL_A)
         for (uint32_t v0 = 0; v0 < n_visit; v0 += 32) {
@@ -516,7 +541,8 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     act_row[s] = (uint8_t)action;  // pkb_step_random(actions_out): copied out with the tile's outputs
                 } else if (ENV && env_round) {  // an opponent's move: only envs whose loop is still running are visited
-                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.round_base + env_round - 1u);
+                    const uint32_t word = sample_word(a.gc.seed, a.gc.env_id_base + (a.env_ids ? a.env_ids[env] : (uint32_t)env),
+                                                      a.round_base + a.env_round_offset + env_round - 1u);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                 } else {
                     action = act_row[s];
@@ -550,10 +576,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         PKB_WTICK(1);
         // the previous tile's store has had pass A's time to finish: publish it without waiting
         // one look at the next tile's epoch while passes C and D run: the acquire's round trip is off the load's path
-        if (lane == 0) handed_over = next < a.num_tiles && ld_acquire_u32(&d.epoch[next]) == launch;
-#ifdef PKB_PUBLISH_AFTER_A
-        if (lane == 0 && stored != 0xffffffffu) { epoch_publish(&d.epoch[stored], launch + 1u); stored = 0xffffffffu; }
-#endif
+        if (lane == 0) handed_over = next < num_tiles && !a.no_epoch && ld_acquire_u32(&d.epoch[next]) == launch;
 
         // Passes C and D repeat while hands keep ending inside this step (all-in blinds: a slot whose next hand
         // cannot be acted on either); such slots go round again through the SAME code, side by side.
@@ -574,7 +597,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                     s = list_s[i];
                     x = load_seats<P>(v, s);
                     ++tl.shows;
-                    showdown_deal<P>(v, s, a.gc.seed, a.gc.env_id_base + (uint32_t)(base + s), ep[s]);
+                    showdown_deal<P>(v, s, a.gc.seed, a.gc.env_id_base + (ENV && a.env_ids ? a.env_ids[base + s] : (uint32_t)(base + s)), ep[s]);
                 }
                 if constexpr (P == 2) {  // both seats of every hand: lane pairs
                     __syncwarp();
@@ -614,7 +637,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 if (i < n_e) {
                     entry = list_e[i];
                     const int s = (int)(entry & 255u);
-                    const size_t env = base + s;
+                    const size_t env = ENV && a.env_ids ? (size_t)a.env_ids[base + s] : base + s;  // the env's index in the handle's planes
                     Seats x = load_seats<P>(v, s);
                     Ctl c = unpack_ctl(entry >> 8);
                     Meta m = unpack_meta(v.meta[s]);
@@ -671,11 +694,11 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 const int s = env_round ? (int)(have ? pend[v0 + lane] : 0u) : (int)(v0 + lane);
                 bool pending = false;
                 if (have) {
-                    const size_t env = base + s;
+                    const size_t env = a.env_ids ? (size_t)a.env_ids[base + s] : base + s;  // the env's index in the handle's planes
                     const uint32_t ec_in = env_round == 0 ? (uint32_t)EC_AGENT_STEP : (uint32_t)act_row[s];
                     Seats x = load_seats<P>(v, s);
                     Meta m = unpack_meta(v.meta[s]);
-                    const bool cap_hit = env_round + 1u >= (uint32_t)ENV_ROUND_CAP;
+                    const bool cap_hit = a.env_round_offset + env_round + 1u >= (uint32_t)ENV_ROUND_CAP;
                     uint32_t ec = env_advance<P>(ec_in, out_f[s], x, m.act, cap_hit);
                     if (ec & EC_REDO) {  // `if done: self.game.reset()` (game_env.py:27)
                         ep[s] += 1;
@@ -699,24 +722,39 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             env_more = n_pend != 0;
             ++env_round;
             __syncwarp();
+            if (env_more && a.env_round_cap && env_round > a.env_round_cap) {
+                // this launch's share of the opponent rounds is played: the envs still inside their loops go to the next phase
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(a.strag_count, n_pend);
+                at = __shfl_sync(FULL, at, 0);
+                for (uint32_t i = lane; i < n_pend; i += 32) {
+                    const int s = pend[i];
+                    a.strag_ids[at + i] = a.env_ids ? a.env_ids[base + s] : (uint32_t)(base + s);
+                    a.strag_ctl[at + i] = act_row[s];
+                }
+                env_more = false;
+            }
         }
         // ---- store: make the generic-proxy writes visible to the async proxy, then push the rows back
         fence_async_smem();
         __syncwarp();
         if (SAMPLE && a.actions_out)
-            for (int s = lane; s < T && base + s < d.n; s += 32) a.actions_out[base + s] = act_row[s];
+            for (int s = lane; s < T && base + s < n_envs; s += 32) a.actions_out[base + s] = act_row[s];
         if (a.packed) {  // the compact output: FOLD and ALL_IN are always valid (game.py:367), so five mask bits say it all
-            for (int s = lane; s < T && base + s < d.n; s += 32)
+            for (int s = lane; s < T && base + s < n_envs; s += 32)
                 a.packed[base + s] = (uint8_t)((out_f[s] & 7u) | (out_v[s] >> 1 & 31u) << 3);
         }
-        if (out_words && base + T <= d.n) {  // the two output rows: one 32-bit store per lane and 32 slots
+        if (ENV && a.env_ids) {  // continue phase: the slots are a packed selection of the handle's envs
+            for (int s = lane; s < T && base + s < n_envs; s += 32)
+                if (a.valid) a.valid[a.env_ids[base + s]] = out_v[s];
+        } else if (out_words && base + T <= n_envs) {  // the two output rows: one 32-bit store per lane and 32 slots
 #pragma unroll
             for (int w = lane; w < T / 4; w += 32) {
                 if (a.flags) reinterpret_cast<uint32_t*>(a.flags + base)[w] = reinterpret_cast<const uint32_t*>(out_f)[w];
                 if (a.valid) reinterpret_cast<uint32_t*>(a.valid + base)[w] = reinterpret_cast<const uint32_t*>(out_v)[w];
             }
         } else {
-            for (int s = lane; s < T && base + s < d.n; s += 32) {
+            for (int s = lane; s < T && base + s < n_envs; s += 32) {
                 if (a.flags) a.flags[base + s] = out_f[s];
                 if (a.valid) a.valid[base + s] = out_v[s];
             }
@@ -736,7 +774,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         wt_acc[5] += 1;
 #endif
     }
-    if (lane == 0 && stored != 0xffffffffu) epoch_publish(&d.epoch[stored], launch + 1u);
+    if (lane == 0 && stored != 0xffffffffu && !a.no_epoch) epoch_publish(&d.epoch[stored], launch + 1u);
 #ifdef PKB_TIMING
     {
         const uint32_t gw = blockIdx.x * L::WARPS + warp;
@@ -757,6 +795,44 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
     }
 #endif
     if (a.gc.track_stats) reduce_stats<P>(d, tl);
+}
+
+// --------------------------------------------------------------------------------------------
+// PokerGameEnv.step in phases: the envs whose opponents are still playing when a phase has used up its rounds are copied
+// into a scratch arena, packed densely, and copied back after the next phase has stepped them there
+// --------------------------------------------------------------------------------------------
+template <int P, bool TO_SCRATCH>
+__global__ void env_move_kernel(DevState m, DevState sc, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ count)
+{
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t e = ids[i];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if (TO_SCRATCH) {
+                sc.cr[p * sc.stride + i] = m.cr[p * m.stride + e];
+                sc.bt[p * sc.stride + i] = m.bt[p * m.stride + e];
+                sc.pd[p * sc.stride + i] = m.pd[p * m.stride + e];
+            } else {
+                m.cr[p * m.stride + e] = sc.cr[p * sc.stride + i];
+                m.bt[p * m.stride + e] = sc.bt[p * sc.stride + i];
+                m.pd[p * m.stride + e] = sc.pd[p * sc.stride + i];
+            }
+        }
+        if (TO_SCRATCH) {
+            sc.mr[i] = m.mr[e];
+            sc.sm[i] = m.sm[e];
+            sc.meta[i] = m.meta[e];
+            sc.hand[i] = m.hand[e];
+            sc.episode[i] = m.episode[e];
+        } else {
+            m.mr[e] = sc.mr[i];
+            m.sm[e] = sc.sm[i];
+            m.meta[e] = sc.meta[i];
+            m.hand[e] = sc.hand[i];
+            m.episode[e] = sc.episode[i];
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1214,6 +1290,14 @@ struct pkb_env {
     bool pipelined;      // step launches may overlap their predecessor's tail (programmatic dependent launch)
     bool last_was_step;  // the handle's previous launch was a step launch (on last_stream)
     unsigned long long last_capture;  // id of the stream capture that launch was recorded into (0: launched live)
+    // PokerGameEnv.step in phases (env_step_phases): scratch arena for the envs whose loop outlasts a phase
+    int64_t env_phase_min;   // handles with at least this many envs step their env mode in phases (< 0: never)
+    void* scratch;
+    DevState sd;             // the scratch arena's planes (payoffs and statistics are the handle's own)
+    TileMaps smaps;
+    uint32_t* strag_count[2];
+    uint32_t* strag_ids[2];
+    uint8_t* strag_ctl[2];
 };
 
 static thread_local std::string g_error;
@@ -1494,6 +1578,8 @@ int pkb_create(const pkb_config* cfg, pkb_env** out)
         delete h;
         return fail("pkb_create: cuTensorMapEncodeTiled failed");
     }
+    h->env_phase_min = 16384;
+    h->scratch = nullptr;
     h->has_last = false;
     h->last_stream = nullptr;
     h->pipelined = getenv("PKB_NO_PDL") == nullptr;
@@ -1513,6 +1599,7 @@ int pkb_destroy(pkb_env* h)
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->arena);  // waits for the handle's launches
+    cudaFree(h->scratch);
     cudaEventDestroy(h->order_event);
     delete h;
     return 0;
@@ -1564,7 +1651,7 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     if (!h) return fail("pkb_step: null handle");
     if (!sample && !actions && !actions_u8 && !actions_u4) return fail("pkb_step: null actions");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
-    StepArgs a;
+    StepArgs a{};  // every field the call does not set is zero (null pointers, no phases, tile hand-over on)
     a.maps = h->maps;
     a.d = h->d;
     a.gc = h->gc;
@@ -1610,6 +1697,57 @@ int pkb_step_u8(pkb_env* h, const uint8_t* actions, uint8_t* flags, uint8_t* val
     return step_common(h, false, 0, nullptr, nullptr, actions, nullptr, flags, valid, stream);
 }
 
+// opponent rounds per phase of PokerGameEnv.step (0: until every loop has returned; ENV_ROUND_CAP still applies)
+constexpr int ENV_PHASES = 4;
+constexpr uint32_t ENV_PHASE_ROUNDS[ENV_PHASES] = {6, 12, 32, 0};
+
+// the scratch arena of a handle: the planes a step launch moves (same layout, same stride), two straggler lists
+static int env_scratch_create(pkb_env* h)
+{
+    const int P = h->cfg.num_players;
+    const uint64_t stride = h->d.stride;
+    const size_t n_w64 = (size_t)(3 * P + 2) * stride, n_u32 = (size_t)3 * stride;
+    const size_t off_u32 = n_w64 * 8, off_seq = (off_u32 + n_u32 * 4 + 255) / 256 * 256;
+    const size_t off_cnt = off_seq + 256, off_ids = off_cnt + 256, off_ctl = off_ids + 2 * stride * 4;
+    const size_t bytes = off_ctl + 2 * stride;
+    void* mem = nullptr;
+    cudaError_t e = cudaMalloc(&mem, bytes);
+    if (e != cudaSuccess) return fail("pkb_env_step: cudaMalloc (scratch arena)", e);
+    e = cudaMemset(mem, 0, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(mem);
+        return fail("pkb_env_step: cudaMemset (scratch arena)", e);
+    }
+    char* base = static_cast<char*>(mem);
+    double* f = reinterpret_cast<double*>(base);
+    DevState sd = h->d;  // payoffs, statistics: the handle's own
+    sd.cr = f;
+    sd.bt = f + (size_t)P * stride;
+    sd.pd = f + (size_t)2 * P * stride;
+    sd.mr = f + (size_t)3 * P * stride;
+    sd.sm = reinterpret_cast<uint64_t*>(f + (size_t)(3 * P + 1) * stride);
+    uint32_t* u = reinterpret_cast<uint32_t*>(base + off_u32);
+    sd.meta = u;
+    sd.hand = u + stride;
+    sd.episode = u + 2 * stride;
+    sd.seq = reinterpret_cast<unsigned long long*>(base + off_seq);
+    sd.epoch = nullptr;  // scratch launches keep plain stream order (StepArgs::no_epoch)
+    bool maps_ok = false;
+    PKB_DISPATCH_P(P, maps_ok = make_tile_maps<P>(h->smaps, sd));
+    if (!maps_ok) {
+        cudaFree(mem);
+        return fail("pkb_env_step: cuTensorMapEncodeTiled failed (scratch arena)");
+    }
+    h->sd = sd;
+    for (int i = 0; i < 2; ++i) {
+        h->strag_count[i] = reinterpret_cast<uint32_t*>(base + off_cnt) + 16 * i;
+        h->strag_ids[i] = reinterpret_cast<uint32_t*>(base + off_ids) + (size_t)i * stride;
+        h->strag_ctl[i] = reinterpret_cast<uint8_t*>(base + off_ctl) + (size_t)i * stride;
+    }
+    h->scratch = mem;
+    return 0;
+}
+
 // PokerGameEnv.step / reset for every env in one launch (the kernel's env mode)
 static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint8_t* env_mask, uint32_t round_base,
                       const uint32_t* weights, double* reward, uint8_t* done, uint8_t* valid, void* stream)
@@ -1617,7 +1755,7 @@ static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint
     if (!h) return fail("pkb_env: null handle");
     if (!reset && !actions) return fail("pkb_env_step: null actions");
     PKB_CUDA(cudaSetDevice(h->cfg.device));
-    StepArgs a;
+    StepArgs a{};  // every field the call does not set is zero (null pointers, no phases, tile hand-over on)
     a.maps = h->maps;
     a.d = h->d;
     a.gc = h->gc;
@@ -1637,13 +1775,73 @@ static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint
     a.env_mask = env_mask;
     a.reward = reward;
     a.env_done = done;
+    a.env_round_cap = a.env_round_offset = a.no_epoch = 0;
+    a.env_ids = nullptr;
+    a.n_dev = nullptr;
+    a.env_ctl_in = nullptr;
+    a.strag_count = nullptr;
+    a.strag_ids = nullptr;
+    a.strag_ctl = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool phases = !reset && h->env_phase_min >= 0 && h->d.n >= (uint64_t)h->env_phase_min;
+    if (phases && !h->scratch && env_scratch_create(h) != 0) return -1;
     PKB_CUDA(order_on_stream(h, s, true));
     a.wait_prev = step_must_wait(h, s);
     cudaError_t e = cudaSuccess;
+    if (!phases) {
+        PKB_DISPATCH_P(h->cfg.num_players, e = (launch_step<P, false, true>(a, s, h->cfg.device, h->sm_count, false)));
+        if (e != cudaSuccess) return fail("pkb_env: launch", e);
+        h->last_was_step = true;
+        return 0;
+    }
+    // PokerGameEnv.step in phases.  A table whose agent has folded plays its hand out among the opponents, and one whose
+    // agent is broke plays until the game is over, inside the same call (envs/game_env.py:41-52): 5 % of the tables need
+    // more than 6 opponent moves, 1 % more than 28, and a 128-table tile would go round ~35 times for its last few tables
+    // (measured: 8.9 of 32 lanes).  So the launch over the handle's planes stops after ENV_PHASE_ROUNDS[0] opponent
+    // rounds; the envs still inside their loops are copied into a scratch arena, packed densely, stepped there by the
+    // next phase, and copied back.  An env's j-th opponent move draws with the same sampler index in whichever phase
+    // it falls, so the result does not depend on the phases.
+    PKB_CUDA(cudaMemsetAsync(h->strag_count[0], 0, 4, s));
+    a.env_round_cap = ENV_PHASE_ROUNDS[0];
+    a.strag_count = h->strag_count[0];
+    a.strag_ids = h->strag_ids[0];
+    a.strag_ctl = h->strag_ctl[0];
     PKB_DISPATCH_P(h->cfg.num_players, e = (launch_step<P, false, true>(a, s, h->cfg.device, h->sm_count, false)));
     if (e != cudaSuccess) return fail("pkb_env: launch", e);
-    h->last_was_step = true;
+    uint32_t offset = ENV_PHASE_ROUNDS[0];
+    for (int k = 1; k < ENV_PHASES; ++k) {
+        const int cur = (k - 1) & 1, nxt = k & 1;
+        StepArgs b = a;
+        b.maps = h->smaps;
+        b.d = h->sd;
+        b.actions = nullptr;
+        b.env_round_cap = ENV_PHASE_ROUNDS[k];
+        b.env_round_offset = offset;
+        b.no_epoch = 1;
+        b.wait_prev = 1;
+        b.env_ids = h->strag_ids[cur];
+        b.n_dev = h->strag_count[cur];
+        b.env_ctl_in = h->strag_ctl[cur];
+        b.strag_count = h->strag_count[nxt];
+        b.strag_ids = h->strag_ids[nxt];
+        b.strag_ctl = h->strag_ctl[nxt];
+        PKB_CUDA(cudaMemsetAsync(h->strag_count[nxt], 0, 4, s));
+        const unsigned mg = (unsigned)(h->sm_count * 4);
+        PKB_DISPATCH_P(h->cfg.num_players, (env_move_kernel<P, true><<<mg, 256, 0, s>>>(h->d, h->sd, b.env_ids, b.n_dev)));
+        PKB_DISPATCH_P(h->cfg.num_players, e = (launch_step<P, false, true>(b, s, h->cfg.device, h->sm_count, false)));
+        if (e != cudaSuccess) return fail("pkb_env: phase launch", e);
+        PKB_DISPATCH_P(h->cfg.num_players, (env_move_kernel<P, false><<<mg, 256, 0, s>>>(h->d, h->sd, b.env_ids, b.n_dev)));
+        PKB_CUDA(cudaGetLastError());
+        offset += ENV_PHASE_ROUNDS[k];
+    }
+    h->last_was_step = false;  // the last launch wrote the planes outside the tile hand-over: the next step launch waits for it
+    return 0;
+}
+
+int pkb_set_env_phases(pkb_env* h, int64_t min_envs)
+{
+    if (!h) return fail("pkb_set_env_phases: null handle");
+    h->env_phase_min = min_envs;
     return 0;
 }
 

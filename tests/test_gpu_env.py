@@ -179,12 +179,16 @@ def test_q_learning_example_runs(torch_cuda):
     assert score[1] > 0 and stats["invalid"] == 0 and stats["poisoned"] == 0 and stats["hands"] > 0
 
 
-@pytest.mark.parametrize("P,weights", [(3, None), (4, (10, 30, 30, 5, 5, 5, 45)), (2, None)])
-def test_fused_env_step_and_reset_equal_the_reference_loops(torch_cuda, ora, P, weights):
+@pytest.mark.parametrize("P,weights,phases", [(3, None, False), (4, (10, 30, 30, 5, 5, 5, 45), False), (2, None, False),
+                                              (3, None, True), (4, (10, 30, 30, 5, 5, 5, 45), True), (2, None, True),
+                                              (9, None, True)])
+def test_fused_env_step_and_reset_equal_the_reference_loops(torch_cuda, ora, P, weights, phases):
     """pkb_env_step / pkb_env_reset (ONE launch per PokerGameEnv.step / reset, opponents played by the device sampler
     inside the kernel) against game_env.py's loops restated over the oracle, table by table: rewards (bit for bit),
     done / hand_over, the valid mask handed to the agent and the final state.  The j-th opponent move of a table
-    inside call c draws with sampler index c * ENV_ROUND_CAP + j - 1."""
+    inside call c draws with sampler index c * ENV_ROUND_CAP + j - 1.  phases: PokerGameEnv.step as a sequence of
+    launches, the tables whose opponents are still playing after 6 / 18 / 50 moves packed into the scratch arena
+    (pkb_set_env_phases; large handles do that by default)."""
     torch = torch_cuda
     from pokerl_b200 import _native as nat
     from pokerl_b200.agents import RandomAgent
@@ -193,6 +197,7 @@ def test_fused_env_step_and_reset_equal_the_reference_loops(torch_cuda, ora, P, 
     cfg = dict(num_players=P, start_credits=30, big_blind=4, small_blind=2, seed=seed)
     env = PokerGameEnv(agents=[RandomAgent(weights) for _ in range(P - 1)], num_envs=N, **cfg)
     assert env._fused
+    env.game.batch.set_env_phases(0 if phases else -1)
     gen = torch.Generator(device="cuda").manual_seed(3)
     calls = []  # ("reset", mask or None) / ("step", actions, reward, done, hand, valid)
     state = env.reset()
