@@ -168,9 +168,9 @@ int pkb_env_step(pkb_env *h, const int32_t *actions, uint32_t round_base, const 
                  uint8_t *done, uint8_t *valid, void *stream);
 int pkb_env_reset(pkb_env *h, const uint8_t *env_mask, uint32_t round_base, const uint32_t *weights, uint8_t *valid,
                   void *stream);
-/* pkb_env_step on large handles runs in PHASES: the launch over the handle's planes plays six opponent rounds, the envs
+/* pkb_env_step on large handles runs in PHASES: the launch over the handle's planes plays three opponent rounds, the envs
  * whose opponents are still playing after that (an agent that has folded or gone broke; envs/game_env.py:41-52) are
- * packed into a scratch arena and stepped there by follow-up launches (12, 32, then all remaining rounds).  Results do
+ * packed into a scratch arena and stepped there by follow-up launches (6, 12, 24, then all remaining rounds).  Results do
  * not depend on it.  min_envs: handles with at least this many envs use phases (default 16384; 0: always; < 0: never).
  * The scratch arena (the size of the handle's state) is allocated by the first phased call. */
 int pkb_set_env_phases(pkb_env *h, int64_t min_envs);

@@ -1698,8 +1698,29 @@ int pkb_step_u8(pkb_env* h, const uint8_t* actions, uint8_t* flags, uint8_t* val
 }
 
 // opponent rounds per phase of PokerGameEnv.step (0: until every loop has returned; ENV_ROUND_CAP still applies)
-constexpr int ENV_PHASES = 4;
-constexpr uint32_t ENV_PHASE_ROUNDS[ENV_PHASES] = {6, 12, 32, 0};
+constexpr int ENV_MAX_PHASES = 8;
+struct EnvPhases {
+    int count;
+    uint32_t rounds[ENV_MAX_PHASES];
+};
+static const EnvPhases& env_phases()
+{
+    static const EnvPhases ph = [] {
+        EnvPhases p{5, {3, 6, 12, 24, 0}};  // measured on 2^23 four-player tables: 6,12,32,0 10.45 ms per learner step; 3,6,12,24,0 9.87; 4,0 10.9
+        if (const char* e = getenv("PKB_ENV_PHASE_ROUNDS")) {  // tuning: comma-separated rounds per phase, the last one 0
+            p.count = 0;
+            for (const char* q = e; *q && p.count < ENV_MAX_PHASES;) {
+                p.rounds[p.count++] = (uint32_t)strtoul(q, nullptr, 10);
+                q = strchr(q, ',');
+                if (!q) break;
+                ++q;
+            }
+            if (p.count == 0 || p.rounds[p.count - 1] != 0) p = EnvPhases{5, {3, 6, 12, 24, 0}};
+        }
+        return p;
+    }();
+    return ph;
+}
 
 // the scratch arena of a handle: the planes a step launch moves (same layout, same stride), two straggler lists
 static int env_scratch_create(pkb_env* h)
@@ -1797,25 +1818,26 @@ static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint
     // PokerGameEnv.step in phases.  A table whose agent has folded plays its hand out among the opponents, and one whose
     // agent is broke plays until the game is over, inside the same call (envs/game_env.py:41-52): 5 % of the tables need
     // more than 6 opponent moves, 1 % more than 28, and a 128-table tile would go round ~35 times for its last few tables
-    // (measured: 8.9 of 32 lanes).  So the launch over the handle's planes stops after ENV_PHASE_ROUNDS[0] opponent
+    // (measured: 8.9 of 32 lanes).  So the launch over the handle's planes stops after the first phase's opponent
     // rounds; the envs still inside their loops are copied into a scratch arena, packed densely, stepped there by the
     // next phase, and copied back.  An env's j-th opponent move draws with the same sampler index in whichever phase
     // it falls, so the result does not depend on the phases.
     PKB_CUDA(cudaMemsetAsync(h->strag_count[0], 0, 4, s));
-    a.env_round_cap = ENV_PHASE_ROUNDS[0];
+    const EnvPhases& ph = env_phases();
+    a.env_round_cap = ph.rounds[0];
     a.strag_count = h->strag_count[0];
     a.strag_ids = h->strag_ids[0];
     a.strag_ctl = h->strag_ctl[0];
     PKB_DISPATCH_P(h->cfg.num_players, e = (launch_step<P, false, true>(a, s, h->cfg.device, h->sm_count, false)));
     if (e != cudaSuccess) return fail("pkb_env: launch", e);
-    uint32_t offset = ENV_PHASE_ROUNDS[0];
-    for (int k = 1; k < ENV_PHASES; ++k) {
+    uint32_t offset = ph.rounds[0];
+    for (int k = 1; k < ph.count; ++k) {
         const int cur = (k - 1) & 1, nxt = k & 1;
         StepArgs b = a;
         b.maps = h->smaps;
         b.d = h->sd;
         b.actions = nullptr;
-        b.env_round_cap = ENV_PHASE_ROUNDS[k];
+        b.env_round_cap = ph.rounds[k];
         b.env_round_offset = offset;
         b.no_epoch = 1;
         b.wait_prev = 1;
@@ -1832,7 +1854,7 @@ static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint
         if (e != cudaSuccess) return fail("pkb_env: phase launch", e);
         PKB_DISPATCH_P(h->cfg.num_players, (env_move_kernel<P, false><<<mg, 256, 0, s>>>(h->d, h->sd, b.env_ids, b.n_dev)));
         PKB_CUDA(cudaGetLastError());
-        offset += ENV_PHASE_ROUNDS[k];
+        offset += ph.rounds[k];
     }
     h->last_was_step = false;  // the last launch wrote the planes outside the tile hand-over: the next step launch waits for it
     return 0;

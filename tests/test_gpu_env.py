@@ -187,7 +187,7 @@ def test_fused_env_step_and_reset_equal_the_reference_loops(torch_cuda, ora, P, 
     inside the kernel) against game_env.py's loops restated over the oracle, table by table: rewards (bit for bit),
     done / hand_over, the valid mask handed to the agent and the final state.  The j-th opponent move of a table
     inside call c draws with sampler index c * ENV_ROUND_CAP + j - 1.  phases: PokerGameEnv.step as a sequence of
-    launches, the tables whose opponents are still playing after 6 / 18 / 50 moves packed into the scratch arena
+    launches, the tables whose opponents are still playing after 3 / 9 / 21 / 45 moves packed into the scratch arena
     (pkb_set_env_phases; large handles do that by default)."""
     torch = torch_cuda
     from pokerl_b200 import _native as nat
