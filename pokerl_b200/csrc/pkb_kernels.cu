@@ -1804,8 +1804,14 @@ static int env_common(pkb_env* h, bool reset, const int32_t* actions, const uint
     a.strag_ids = nullptr;
     a.strag_ctl = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool phases = !reset && h->env_phase_min >= 0 && h->d.n >= (uint64_t)h->env_phase_min;
-    if (phases && !h->scratch && env_scratch_create(h) != 0) return -1;
+    bool phases = !reset && h->env_phase_min >= 0 && h->d.n >= (uint64_t)h->env_phase_min;
+    if (phases && !h->scratch) {
+        // the scratch arena is allocated by the first phased call; a call that is being recorded into a CUDA graph cannot
+        // allocate, so it runs as one launch (same results) -- call pkb_env_step once before capturing to get the phases
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) phases = false;
+        else if (env_scratch_create(h) != 0) return -1;
+    }
     PKB_CUDA(order_on_stream(h, s, true));
     a.wait_prev = step_must_wait(h, s);
     cudaError_t e = cudaSuccess;
