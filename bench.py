@@ -427,6 +427,19 @@ def run_ours(args, rank, local_rank, world):
             g.step_random(t_idx + i)
     resident_ms = timed(one_batch) / KF
 
+    # ---- rollouts whose intermediate states nobody reads: FUSED steps per launch (pkb_step_random_n).  Every tile of envs
+    # is loaded once, stepped FUSE times in shared memory and stored once; same six batches, same stream, K bench steps =
+    # K * FUSE Game.steps per env.  State, statistics and payoffs are exactly those of single-step launches (GPU test).
+    FUSE = int(os.environ.get("PKB_BENCH_FUSE", "4"))
+    t_fused = t_idx + KF + 16
+
+    def fused_steps():
+        for i in range(K):
+            for gb in batches:
+                gb.step_random(t_fused + i * FUSE, repeat=FUSE)
+    fused_steps()  # warm-up
+    fused_ms = timed(fused_steps)
+
     # ---- end to end through the public API with HOST buffers.  Every step: H2D copy of that step's actions from
     # pinned host memory (two moves per byte), GameBatch.step_packed, D2H copy of its result byte per env (done flags +
     # valid mask) to pinned host memory.  Within a batch, copy-in -> step -> copy-out is a serial chain, so E2E_BATCHES
@@ -555,7 +568,7 @@ def run_ours(args, rank, local_rank, world):
         ql = q_learning_block(args, rank, local_rank, world, timed)
 
     # ---- max over ranks; NCCL reduction of the statistics vector (the only collective)
-    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms] + regions,
+    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms, fused_ms] + regions,
                        dtype=torch.float64, device=dev)
     svec = torch.tensor([stats["steps"], stats["hands"], stats["showdowns"], stats["games"], stats["invalid"],
                          stats["poisoned"]] + stats["payoff_sum"], dtype=torch.float64, device=dev)
@@ -565,8 +578,8 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(svec, op=dist.ReduceOp.SUM)
         dist.all_reduce(s9vec, op=dist.ReduceOp.SUM)
-    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms = vec.tolist()[:7]
-    regions = vec.tolist()[7:]
+    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms, fused_ms = vec.tolist()[:8]
+    regions = vec.tolist()[8:]
     dev_ms = statistics.median(regions)  # median of the per-region maxima over the ranks
     if rank != 0:
         return
@@ -623,6 +636,13 @@ def run_ours(args, rank, local_rank, world):
                        "roofline": {"bound": "hbm", "kernel": "pkb::eval_masks_fast_kernel", "achieved": 12 * eval_rate / world / 1e9,
                                     "peak": peak, "unit": "GB/s", "frac": 12 * eval_rate / world / 1e9 / peak,
                                     "traffic": ncu_traffic("eval_masks_fast_kernel"), "algorithmic_bytes_per_eval": 12}},
+        "fused_steps": {"metric": "env_steps_per_sec", "value": N * RESIDENT_BATCHES * world * K * FUSE / (fused_ms / 1e3),
+                        "unit": "env-steps/s", "steps_per_launch": FUSE, "launches": K * RESIDENT_BATCHES,
+                        "frac": algorithmic_bytes_per_step(P) * N * FUSE / (fused_ms / 1e3 / (K * RESIDENT_BATCHES)) / 1e9 / peak,
+                        "note": f"pkb_step_random_n / GameBatch.step_random(repeat={FUSE}): every launch steps each tile of envs {FUSE} "
+                                "times in shared memory between one load and one store -- for rollouts with device-side agents "
+                                "whose intermediate states nobody reads; the same workload, batches and stream as `value`; `frac` "
+                                "counts the algorithmic bytes of every Game.step although the state crosses HBM once per launch"},
         "exhaustive_eval": {"workload": "all C(52,7) seven-card hands enumerated on chip (BASELINE.json configs[1]), rank 0",
                             "hands": 133784560, "wall_ms": exh_s * 1e3, "value": 133784560 / exh_s, "unit": "7-card evals/s",
                             "matches_reference_histogram_and_checksums": bool(exh_ok),

@@ -174,6 +174,13 @@ int pkb_env_reset(pkb_env *h, const uint8_t *env_mask, uint32_t round_base, cons
  * not depend on it.  min_envs: handles with at least this many envs use phases (default 16384; 0: always; < 0: never).
  * The scratch arena (the size of the handle's state) is allocated by the first phased call. */
 int pkb_set_env_phases(pkb_env *h, int64_t min_envs);
+/* n_steps consecutive pkb_step_random steps (sampler step indices step_idx .. step_idx + n_steps - 1) in ONE launch: every
+ * tile of envs is loaded once, stepped n_steps times in shared memory and stored once, so the state crosses HBM once per
+ * n_steps Game.steps.  The state, the statistics and the payoffs afterwards are exactly those of n_steps single calls;
+ * actions_out / flags / valid (each may be NULL) receive the LAST step's values.  For rollouts with device-side agents
+ * whose intermediate states nobody reads. */
+int pkb_step_random_n(pkb_env *h, uint32_t step_idx, uint32_t n_steps, const uint32_t *weights, int32_t *actions_out,
+                      uint8_t *flags, uint8_t *valid, void *stream);
 /* Sampler alone (K5): actions for the CURRENT state, without stepping. */
 int pkb_sample_actions(pkb_env *h, uint32_t step_idx, const uint32_t *weights, int32_t *actions_out, void *stream);
 /* Game.get_valid_actions(player), game.py:339-383.  player < 0: each env's active player. */

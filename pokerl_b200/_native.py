@@ -84,6 +84,7 @@ SYMBOLS = {
     "pkb_env_reset": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     "pkb_set_env_phases": (C.c_int, [_vp, C.c_int64]),
     "pkb_step_random": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "pkb_step_random_n": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "pkb_sample_actions": (C.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "pkb_valid_actions": (C.c_int, [_vp, _i32, _vp, _vp]),
     "pkb_game_over": (C.c_int, [_vp, _vp, _vp]),

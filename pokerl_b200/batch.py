@@ -260,13 +260,20 @@ class GameBatch:
                                           self._stream()))
         return valid
 
-    def step_random(self, step_idx, weights=None, record_actions=False, flags=None, valid=None):
-        """One step with the on-device random agent (uniform, or integer `weights` per move)."""
+    def step_random(self, step_idx, weights=None, record_actions=False, flags=None, valid=None, repeat=1):
+        """One step with the on-device random agent (uniform, or integer `weights` per move).  repeat = K: K consecutive
+        steps (sampler indices step_idx .. step_idx + K - 1) in one launch -- every tile of envs is stepped K times in
+        shared memory between one load and one store; state, statistics and payoffs are those of K single calls, the
+        outputs are the last step's (pkb_step_random_n)."""
         w = None if weights is None else (C.c_uint32 * nat.NUM_MOVES)(*[int(x) for x in weights])
         flags, valid = self._out(flags, self.flags, "flags"), self._out(valid, self.valid, "valid")
         out = self.actions_taken if record_actions else None
-        nat.check(nat.lib().pkb_step_random(self._h.ptr, int(step_idx) & 0xFFFFFFFF, w, nat.ptr(out), nat.ptr(flags),
-                                            nat.ptr(valid), self._stream()))
+        if int(repeat) != 1:
+            nat.check(nat.lib().pkb_step_random_n(self._h.ptr, int(step_idx) & 0xFFFFFFFF, int(repeat), w, nat.ptr(out),
+                                                  nat.ptr(flags), nat.ptr(valid), self._stream()))
+        else:
+            nat.check(nat.lib().pkb_step_random(self._h.ptr, int(step_idx) & 0xFFFFFFFF, w, nat.ptr(out), nat.ptr(flags),
+                                                nat.ptr(valid), self._stream()))
         return flags, valid
 
     def sample_actions(self, step_idx, weights=None, out=None):

@@ -60,6 +60,7 @@ struct StepArgs {
     uint8_t* flags;
     uint8_t* valid;
     uint32_t step_idx;
+    uint32_t reps;       // device-sampled steps per tile visit (pkb_step_random_n): the tile stays in shared memory between them
     uint32_t use_weights;
     uint32_t weights[NUM_MOVES];
     uint32_t num_tiles;
@@ -449,17 +450,21 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
         constexpr bool SHARED_DRAW = SAMPLE && T <= 160;
         constexpr int NQ = SHARED_DRAW ? T / 32 : 1;
         uint32_t queue[NQ] = {0};
-        if constexpr (SHARED_DRAW) {
-            const uint32_t gid0 = a.gc.env_id_base + (uint32_t)base + (uint32_t)lane;
-            const U4 draw = sample_block(a.gc.seed, gid0, a.step_idx);
-            U4 draw_next{0, 0, 0, 0};
-            if (((gid0 + (uint32_t)(T - 32)) ^ gid0) & ~127u) draw_next = sample_block(a.gc.seed, (gid0 | 127u) + 1u + (gid0 & 31u), a.step_idx);
-            const uint32_t w8[8] = {draw.x, draw.y, draw.z, draw.w, draw_next.x, draw_next.y, draw_next.z, draw_next.w};
-            const uint32_t first = gid0 >> 5 & 3u;  // word of the lane's first slot inside its group's block
+        uint32_t step_now = a.step_idx, rep = 0;  // pkb_step_random_n: the step index of the repetition that is running
+        auto fill_queue = [&](uint32_t step) {
+            if constexpr (SHARED_DRAW) {
+                const uint32_t gid0 = a.gc.env_id_base + (uint32_t)base + (uint32_t)lane;
+                const U4 draw = sample_block(a.gc.seed, gid0, step);
+                U4 draw_next{0, 0, 0, 0};
+                if (((gid0 + (uint32_t)(T - 32)) ^ gid0) & ~127u) draw_next = sample_block(a.gc.seed, (gid0 | 127u) + 1u + (gid0 & 31u), step);
+                const uint32_t w8[8] = {draw.x, draw.y, draw.z, draw.w, draw_next.x, draw_next.y, draw_next.z, draw_next.w};
+                const uint32_t first = gid0 >> 5 & 3u;  // word of the lane's first slot inside its group's block
 #pragma unroll
-            for (int k = 0; k < NQ; ++k)  // slot k takes word first + k of the two blocks (compile-time indices only: registers)
-                queue[k] = first == 0 ? w8[k & 7] : first == 1 ? w8[(k + 1) & 7] : first == 2 ? w8[(k + 2) & 7] : w8[(k + 3) & 7];
-        }
+                for (int k = 0; k < NQ; ++k)  // slot k takes word first + k of the two blocks (compile-time indices only: registers)
+                    queue[k] = first == 0 ? w8[k & 7] : first == 1 ? w8[(k + 1) & 7] : first == 2 ? w8[(k + 2) & 7] : w8[(k + 3) & 7];
+            }
+        };
+        fill_queue(step_now);
         // The previous tile's store was issued just before this tile's load: waiting for it to be performed and releasing
         // its epoch (a GPU-scope fence) costs about what the load takes, and the warp has nothing else to do until then.
         if (lane == 0 && stored != 0xffffffffu && !a.no_epoch) epoch_publish(&d.epoch[stored], launch + 1u);
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
                 const uint32_t vm = SAMPLE ? m.vm : valid_mask_from(hb, credit, v.mr[s]);
                 int action;
                 if (SAMPLE) {
-                    const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, a.step_idx);
+                    const uint32_t word = SHARED_DRAW ? queue[0] : sample_word(a.gc.seed, a.gc.env_id_base + (uint32_t)env, step_now);
                     action = a.use_weights ? pick_weighted(word, vm, a.weights) : pick_uniform(word, vm);
                     act_row[s] = (uint8_t)action;  // pkb_step_random(actions_out): copied out with the tile's outputs
                 } else if (ENV && env_round) {  // an opponent's move: only envs whose loop is still running are visited
@@ -681,7 +686,14 @@ __global__ void __launch_bounds__(WarpTile<P>::THREADS, WarpTile<P>::MIN_BLOCKS)
             n_s = m_s;
         }
 
-            if (!ENV) break;
+            if (!ENV) {
+                // pkb_step_random_n: the next Game.step of the same tile, straight from shared memory -- its load and its
+                // store are paid once per visit instead of once per step
+                if (!SAMPLE || ++rep >= a.reps) break;
+                step_now = a.step_idx + rep;
+                fill_queue(step_now);
+                continue;
+            }
             // ---- PokerGameEnv control (envs/game_env.py:20-54): what this round's step means for every env of the tile
             __threadfence_block();  // the payoff plane is written with plain stores by the lanes of pass D and read here
             __syncwarp();
@@ -1646,7 +1658,7 @@ int pkb_reset(pkb_env* h, const uint8_t* env_mask, void* stream)
 
 static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_t* weights, const int32_t* actions,
                        const uint8_t* actions_u8, int32_t* actions_out, uint8_t* flags, uint8_t* valid, void* stream,
-                       const uint8_t* actions_u4 = nullptr, uint8_t* packed = nullptr)
+                       const uint8_t* actions_u4 = nullptr, uint8_t* packed = nullptr, uint32_t reps = 1)
 {
     if (!h) return fail("pkb_step: null handle");
     if (!sample && !actions && !actions_u8 && !actions_u4) return fail("pkb_step: null actions");
@@ -1668,6 +1680,7 @@ static int step_common(pkb_env* h, bool sample, uint32_t step_idx, const uint32_
     a.flags = flags;
     a.valid = valid;
     a.step_idx = step_idx;
+    a.reps = reps;
     a.use_weights = weights ? 1u : 0u;
     for (int i = 0; i < NUM_MOVES; ++i) a.weights[i] = weights ? weights[i] : 1u;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1894,6 +1907,13 @@ int pkb_step_random(pkb_env* h, uint32_t step_idx, const uint32_t* weights, int3
                     uint8_t* valid, void* stream)
 {
     return step_common(h, true, step_idx, weights, nullptr, nullptr, actions_out, flags, valid, stream);
+}
+
+int pkb_step_random_n(pkb_env* h, uint32_t step_idx, uint32_t n_steps, const uint32_t* weights, int32_t* actions_out, uint8_t* flags,
+                      uint8_t* valid, void* stream)
+{
+    if (n_steps == 0) return 0;
+    return step_common(h, true, step_idx, weights, nullptr, nullptr, actions_out, flags, valid, stream, nullptr, nullptr, n_steps);
 }
 
 int pkb_sample_actions(pkb_env* h, uint32_t step_idx, const uint32_t* weights, int32_t* actions_out, void* stream)

@@ -347,3 +347,37 @@ def test_step_launches_replayed_from_a_cuda_graph(torch_cuda, ora):
     g.step_random(99)  # and a live launch after the graph
     o.run_random(99, 1)
     states_equal(g, o, "live launch after the replays")
+
+
+@pytest.mark.parametrize("P,K", [(2, 4), (2, 7), (4, 3), (9, 4)])
+def test_repeated_steps_in_one_launch_equal_single_steps(torch_cuda, ora, P, K):
+    """pkb_step_random_n: K device-sampled steps per tile visit (the tile stays in shared memory between them) leave
+    exactly the state, statistics and payoffs of K single pkb_step_random calls -- and of the oracle; the outputs are
+    the last step's.  Ragged batch size, unequal stacks and weights for nine players."""
+    torch = torch_cuda
+    from pokerl_b200 import GameBatch
+    N, rounds = 3000, 8
+    start = 100 if P != 9 else [20 * (i + 1) for i in range(9)]
+    w = None if P != 9 else [10, 30, 30, 5, 5, 5, 45]
+    a = GameBatch(N, P, start, 2, 1, seed=5, auto_reset=True)
+    b = GameBatch(N, P, start, 2, 1, seed=5, auto_reset=True)
+    o = ora.OracleBatch(N, P, start, 2, 1, seed=5, auto_reset=True)
+    a.reset(); b.reset(); o.reset()
+    for r in range(rounds):
+        for k in range(K):
+            fa, va = a.step_random(r * K + k, w, record_actions=True)
+        acts_a = a.actions_taken.clone()
+        fb, vb = b.step_random(r * K, w, record_actions=True, repeat=K)
+        assert torch.equal(fa, fb) and torch.equal(va, vb) and torch.equal(acts_a, b.actions_taken), r
+    o.run_random(0, rounds * K, w)
+    ea, eb, eo = a.export(), b.export(), o.export()
+    for k in ea:
+        assert np.array_equal(np.ascontiguousarray(ea[k]).view(np.uint8), np.ascontiguousarray(eb[k]).view(np.uint8)), k
+    for k in ("credits", "bets", "pending", "payoffs", "minraise"):
+        assert np.array_equal(np.ascontiguousarray(eb[k]).view(np.uint64), np.ascontiguousarray(eo[k]).view(np.uint64)), k
+    for k in ("states", "turn", "hand", "dealer", "sb", "bb", "active", "episode"):
+        assert np.array_equal(eb[k], eo[k]), k
+    sa, sb = a.stats(), b.stats()
+    assert all(sa[k] == sb[k] for k in ("steps", "hands", "showdowns", "games", "invalid", "poisoned")) and sb["steps"] == N * rounds * K
+    # the payoff sums are f64 accumulations whose order differs (per-thread tallies over K steps, then atomics): equal to rounding
+    assert np.allclose(sa["payoff_sum"], sb["payoff_sum"], rtol=1e-12, atol=1e-9)
