@@ -530,6 +530,11 @@ def run_ours(args, rank, local_rank, world):
         for i in range(K9):
             g9.step_random(1000 + i, NINE["weights"])
     nine_ms = timed(nine_steps)
+
+    def nine_fused():
+        for i in range(K9):
+            g9.step_random(5000 + i * FUSE, NINE["weights"], repeat=FUSE)
+    nine_fused_ms = timed(nine_fused)
     g9.set_pipelining(False)
     nine_unpipelined_ms = timed(nine_steps) / K9
     s9 = g9.stats()
@@ -568,7 +573,7 @@ def run_ours(args, rank, local_rank, world):
         ql = q_learning_block(args, rank, local_rank, world, timed)
 
     # ---- max over ranks; NCCL reduction of the statistics vector (the only collective)
-    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms, fused_ms] + regions,
+    vec = torch.tensor([dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms, fused_ms, nine_fused_ms] + regions,
                        dtype=torch.float64, device=dev)
     svec = torch.tensor([stats["steps"], stats["hands"], stats["showdowns"], stats["games"], stats["invalid"],
                          stats["poisoned"]] + stats["payoff_sum"], dtype=torch.float64, device=dev)
@@ -578,8 +583,8 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(svec, op=dist.ReduceOp.SUM)
         dist.all_reduce(s9vec, op=dist.ReduceOp.SUM)
-    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms, fused_ms = vec.tolist()[:8]
-    regions = vec.tolist()[8:]
+    dev_ms, resident_ms, e2e_s, eval_ms, unpipelined_ms, nine_ms, nine_unpipelined_ms, fused_ms, nine_fused_ms = vec.tolist()[:9]
+    regions = vec.tolist()[9:]
     dev_ms = statistics.median(regions)  # median of the per-region maxima over the ranks
     if rank != 0:
         return
@@ -631,6 +636,9 @@ def run_ours(args, rank, local_rank, world):
                         "roofline": {"bound": "hbm", "kernel": "pkb::step_warp_kernel<9,true>", "achieved": nine_gbs, "peak": peak,
                                      "unit": "GB/s", "frac": nine_gbs / peak, "algorithmic_bytes_per_env_step": b9,
                                      "unpipelined_launch_us": nine_unpipelined_ms * 1e3, "traffic": ncu_traffic("step_kernel_p9")},
+                        "fused_steps": {"steps_per_launch": FUSE, "value": NINE["global_envs"] * K9 * FUSE / (nine_fused_ms / 1e3),
+                                        "unit": "env-steps/s",
+                                        "frac": b9 * (NINE["global_envs"] / world) * K9 * FUSE / (nine_fused_ms / 1e3) / 1e9 / peak},
                         "stats": dict(zip(("steps", "hands", "showdowns", "games", "invalid", "poisoned"), s9vec.tolist()))},
         "hand_evals": {"metric": "hand_evals_per_sec", "value": eval_rate, "unit": "7-card evals/s", "hands": n_hands,
                        "roofline": {"bound": "hbm", "kernel": "pkb::eval_masks_fast_kernel", "achieved": 12 * eval_rate / world / 1e9,
