@@ -430,7 +430,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- rollouts whose intermediate states nobody reads: FUSED steps per launch (pkb_step_random_n).  Every tile of envs
     # is loaded once, stepped FUSE times in shared memory and stored once; same six batches, same stream, K bench steps =
     # K * FUSE Game.steps per env.  State, statistics and payoffs are exactly those of single-step launches (GPU test).
-    FUSE = int(os.environ.get("PKB_BENCH_FUSE", "4"))
+    FUSE = int(os.environ.get("PKB_BENCH_FUSE", "8"))
     t_fused = t_idx + KF + 16
 
     def fused_steps():

@@ -1,6 +1,6 @@
 // eval_lab.cu -- stand-alone bench of batch-evaluator variants (profiles/ tool, not part of the product).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I pokerl_b200/csrc -o gpurun_out/eval_lab profiles/eval_lab.cu
-//   gpurun_out/eval_lab [log2 hands]
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I pokerl_b200/csrc -o profiles/_bin/eval_lab profiles/eval_lab.cu
+//   profiles/_bin/eval_lab [log2 hands] [cards per hand, 0 = mixed]   (profiles/_bin/ is git-ignored and travels with gpurun)
 // Every variant's output is compared with eval_mask52 (the bitmask evaluator) on all hands.
 #include <cstdio>
 #include <cstdlib>

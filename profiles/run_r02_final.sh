@@ -15,6 +15,7 @@ python profiles/exhaustive_bench.py > gpurun_out/r02/exhaustive_bench.log 2>&1
 python profiles/ql_breakdown.py > gpurun_out/r02/ql_breakdown.log 2>&1
 PKB_ENV_PHASE_ROUNDS=0 python profiles/ql_breakdown.py > gpurun_out/r02/ql_breakdown_one_phase.log 2>&1
 python profiles/nine_mix_probe.py > gpurun_out/r02/nine_mix_probe.log 2>&1
+python profiles/repeat_probe.py > gpurun_out/r02/repeat_probe.log 2>&1
 # launch list of the bench command (serialised, cold cache: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02/ncu_launches.log 2>&1
