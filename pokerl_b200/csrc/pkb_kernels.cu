@@ -1094,6 +1094,35 @@ PKB_D uint32_t eval7_fast_dev(uint32_t lo, uint32_t hi, const uint32_t* s_klo, c
     return s_vals[s_dense16[fast_slot(sum, s_disp[fast_bucket(sum)])]];
 }
 
+// the block's copy of the tables: [128][32] low-part keys | [64][32] high-part keys | first hash level | the warps' rings |
+// 16-bit class slots | class -> value
+struct EvalFastSmem {
+    uint32_t* klo;
+    uint32_t* khi;
+    uint8_t* disp;
+    uint32_t* queue;
+    uint16_t* dense16;
+    uint32_t* vals;
+};
+PKB_D EvalFastSmem stage_fast_tables(uint8_t* smem, const EvalFastTables& t)
+{
+    constexpr int THREADS = EVAL_FAST_THREADS, WARPS = THREADS / 32, QSIZE = EVAL_FAST_QSIZE;
+    EvalFastSmem m;
+    m.klo = reinterpret_cast<uint32_t*>(smem);
+    m.khi = m.klo + 128 * 32;
+    m.disp = reinterpret_cast<uint8_t*>(m.khi + 64 * 32);
+    m.queue = reinterpret_cast<uint32_t*>(m.disp + EVAL_FAST_BUCKETS);
+    m.dense16 = reinterpret_cast<uint16_t*>(m.queue + WARPS * QSIZE);
+    m.vals = reinterpret_cast<uint32_t*>(m.dense16 + EVAL_DENSE_SIZE);
+    for (int i = threadIdx.x; i < 128 * 32; i += THREADS) m.klo[i] = t.klo[i >> 5];
+    for (int i = threadIdx.x; i < 64 * 32; i += THREADS) m.khi[i] = t.khi[i >> 5];
+    for (int i = threadIdx.x; i < (int)EVAL_FAST_BUCKETS / 16; i += THREADS) reinterpret_cast<uint4*>(m.disp)[i] = reinterpret_cast<const uint4*>(t.disp)[i];
+    for (int i = threadIdx.x; i < (int)EVAL_DENSE_SIZE / 8; i += THREADS) reinterpret_cast<uint4*>(m.dense16)[i] = reinterpret_cast<const uint4*>(t.dense16)[i];
+    for (int i = threadIdx.x; i < (int)t.nvals; i += THREADS) m.vals[i] = t.vals[i];
+    __syncthreads();
+    return m;
+}
+
 // ranks the `count` (<= 32) hands whose indices wait at q[head ..] with the select evaluator; one out-of-line copy
 __device__ __noinline__ void eval_fast_drain(const uint32_t* q, uint32_t head, uint32_t count, const uint64_t* __restrict__ masks,
                                              uint32_t* __restrict__ out)
@@ -1112,18 +1141,11 @@ eval_masks_fast_kernel(const uint64_t* __restrict__ masks, uint64_t n, uint32_t*
 {
     constexpr int THREADS = EVAL_FAST_THREADS, WARPS = THREADS / 32, HPT = EVAL_FAST_HPT, QSIZE = EVAL_FAST_QSIZE;
     extern __shared__ __align__(128) uint8_t fast_smem[];
-    uint32_t* s_klo = reinterpret_cast<uint32_t*>(fast_smem);                    // [128][32]
-    uint32_t* s_khi = s_klo + 128 * 32;                                         // [64][32]
-    uint8_t* s_disp = reinterpret_cast<uint8_t*>(s_khi + 64 * 32);              // [EVAL_FAST_BUCKETS]
-    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_disp + EVAL_FAST_BUCKETS);  // [WARPS][QSIZE]
-    uint16_t* s_dense16 = reinterpret_cast<uint16_t*>(s_queue + WARPS * QSIZE);  // [EVAL_DENSE_SIZE]
-    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_dense16 + EVAL_DENSE_SIZE);  // [nvals]
-    for (int i = threadIdx.x; i < 128 * 32; i += THREADS) s_klo[i] = t.klo[i >> 5];
-    for (int i = threadIdx.x; i < 64 * 32; i += THREADS) s_khi[i] = t.khi[i >> 5];
-    for (int i = threadIdx.x; i < (int)EVAL_FAST_BUCKETS / 16; i += THREADS) reinterpret_cast<uint4*>(s_disp)[i] = reinterpret_cast<const uint4*>(t.disp)[i];
-    for (int i = threadIdx.x; i < (int)EVAL_DENSE_SIZE / 8; i += THREADS) reinterpret_cast<uint4*>(s_dense16)[i] = reinterpret_cast<const uint4*>(t.dense16)[i];
-    for (int i = threadIdx.x; i < (int)t.nvals; i += THREADS) s_vals[i] = t.vals[i];
-    __syncthreads();
+    const EvalFastSmem sm = stage_fast_tables(fast_smem, t);
+    const uint32_t *s_klo = sm.klo, *s_khi = sm.khi, *s_vals = sm.vals;
+    const uint8_t* s_disp = sm.disp;
+    const uint16_t* s_dense16 = sm.dense16;
+    uint32_t* s_queue = sm.queue;
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, lane4 = lane * 4, lt = (1u << lane) - 1u;
     const uint64_t trips = n / (32 * HPT), wstride = (uint64_t)gridDim.x * WARPS;
     uint32_t head = 0, tail = 0;
@@ -1243,6 +1265,60 @@ eval_exhaustive_kernel(int k, uint64_t first, uint64_t count, uint32_t* __restri
         const uint32_t mine = (uint32_t)(cats >> (6 * cat)) & 63u;
         const uint32_t w = __reduce_add_sync(0xffffffffu, mine);
         if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[cat], (unsigned long long)w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 11 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x < 2) atomicAdd(&sums[threadIdx.x], s_sum[threadIdx.x]);
+}
+
+// All C(52,7) hands through the streaming evaluator's tables: one 1024-thread block per SM, every lane ranks chunks of
+// EXH_CHUNK consecutive hands.  Neighbouring lanes enumerate neighbouring ranges, whose hands share their high cards, so a
+// warp's hands are rare (a flush suit, ...) nearly all together or not at all: the select evaluator runs in place here,
+// no queue (with random hands the same branch halves the throughput, eval_masks_fast_kernel).
+__global__ void __launch_bounds__(EVAL_FAST_THREADS, 1)
+eval_exhaustive7_kernel(uint64_t first, uint64_t count, uint32_t* __restrict__ out, unsigned long long* hist, unsigned long long* sums,
+                        EvalFastTables t)
+{
+    constexpr int WARPS = EVAL_FAST_THREADS / 32;
+    extern __shared__ __align__(128) uint8_t fast_smem[];
+    __shared__ unsigned long long s_hist[11], s_sum[2];
+    if (threadIdx.x < 11) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_sum[threadIdx.x] = 0;
+    const EvalFastSmem sm = stage_fast_tables(fast_smem, t);
+    const uint32_t lane = threadIdx.x & 31, lane4 = lane * 4;
+    const uint64_t chunks = (count + EXH_CHUNK - 1) / EXH_CHUNK, wstride = (uint64_t)gridDim.x * WARPS * 32;
+    unsigned long long sum_a = 0, sum_b = 0;
+    for (uint64_t cb = ((uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * 32; cb < chunks; cb += wstride) {
+        const uint64_t lo = (cb + lane) * EXH_CHUNK;
+        const int todo = lo < count ? (int)(count - lo < EXH_CHUNK ? count - lo : EXH_CHUNK) : 0;
+        unsigned long long cats = 0;  // 6-bit counters per category: at most EXH_CHUNK = 32 per chunk
+        if (todo) {
+            uint64_t m = unrank_colex(first + lo, 7);
+            for (int j = 0; j < todo; ++j) {
+                uint32_t rare;
+                uint32_t p = eval7_fast_dev((uint32_t)m, (uint32_t)(m >> 32), sm.klo, sm.khi, lane4, sm.disp, sm.dense16, sm.vals, rare);
+                if (rare) p = eval_mask52_sel(m);
+                if (out) out[lo + j] = p;
+                cats += 1ull << (6 * (p >> 20));
+                sum_a += p;
+                sum_b += (unsigned long long)p * (m % 1000003ull);
+                const uint64_t c = m & (0 - m), r = m + c;  // next mask with the same popcount (Gosper)
+                m = (((r ^ m) >> 2) >> (__ffsll((long long)c) - 1)) | r;
+            }
+        }
+        for (int cat = 1; cat <= 9; ++cat) {  // seven cards: categories 1..9
+            const uint32_t w = __reduce_add_sync(0xffffffffu, (uint32_t)(cats >> (6 * cat)) & 63u);
+            if (lane == 0 && w) atomicAdd(&s_hist[cat], (unsigned long long)w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_a += __shfl_xor_sync(0xffffffffu, sum_a, o);
+        sum_b += __shfl_xor_sync(0xffffffffu, sum_b, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_sum[0], sum_a);
+        atomicAdd(&s_sum[1], sum_b);
     }
     __syncthreads();
     if (threadIdx.x < 11 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
@@ -2182,6 +2258,8 @@ static cudaError_t ensure_eval_fast_tables(EvalFastTables* out)
         free(host);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(eval_masks_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_fast_smem(nvals));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(eval_exhaustive7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_fast_smem(nvals));
         if (e != cudaSuccess) {
             cudaFree(dptr);
             return e;
@@ -2263,10 +2341,23 @@ int pkb_eval_exhaustive(int32_t k, uint64_t first, uint64_t count, uint64_t* his
     unsigned long long* d_acc = nullptr;
     PKB_CUDA(cudaMalloc(&d_acc, 13 * 8));
     cudaError_t e = cudaMemsetAsync(d_acc, 0, 13 * 8, s);
+    static const bool use_hash3 = getenv("PKB_EVAL_IMPL") && !strcmp(getenv("PKB_EVAL_IMPL"), "hash3");
     if (e == cudaSuccess && count) {
         const uint64_t threads = (count + EXH_CHUNK - 1) / EXH_CHUNK;
-        eval_exhaustive_kernel<<<blocks_for(threads, 256), 256, 0, s>>>(k, first, count, out, d_acc, d_acc + 11, t);
-        e = cudaGetLastError();
+        if (k == 7 && !use_hash3 && threads >= 4096) {  // the streaming evaluator's tables, one block per SM
+            EvalFastTables ft;
+            e = ensure_eval_fast_tables(&ft);
+            int dev = 0, sms = 0;
+            if (e == cudaSuccess) e = cudaGetDevice(&dev);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e == cudaSuccess) {
+                eval_exhaustive7_kernel<<<(unsigned)sms, EVAL_FAST_THREADS, eval_fast_smem(ft.nvals), s>>>(first, count, out, d_acc, d_acc + 11, ft);
+                e = cudaGetLastError();
+            }
+        } else {
+            eval_exhaustive_kernel<<<blocks_for(threads, 256), 256, 0, s>>>(k, first, count, out, d_acc, d_acc + 11, t);
+            e = cudaGetLastError();
+        }
     }
     unsigned long long host[13];
     if (e == cudaSuccess) e = cudaMemcpyAsync(host, d_acc, sizeof host, cudaMemcpyDeviceToHost, s);
