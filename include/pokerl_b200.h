@@ -207,7 +207,9 @@ int pkb_deal(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t hand, in
 /* eval_hand on n hands of k cards each (0 <= k <= 7), judger.py:7-99.  cards: device u8[n][k]
  * card values (duplicates allowed, as in the reference's own tests).  out: device u32[n] packed. */
 int pkb_eval_cards(const uint8_t *cards, int32_t k, uint64_t n, uint32_t *out, void *stream);
-/* eval_hand on n hands given as 52-bit id masks (<= 7 bits set).  masks: device u64[n]. */
+/* eval_hand on n hands given as 52-bit id masks (<= 7 bits set).  masks: device u64[n].  (Batches of >= 2^17 hands in
+ * 16-byte aligned arrays take the streaming evaluator -- a perfect hash of the rank multiset held in shared memory, the
+ * few hands it does not cover ranked in a second pass per warp; the result is the same word either way.) */
 int pkb_eval_masks(const uint64_t *masks, uint64_t n, uint32_t *out, void *stream);
 /* All C(52,k) hands (k = 1..7), enumerated on device in colex order of the id mask.
  * hist: host u64[11] by category; sums: host u64[2] = {sum packed, sum packed*(mask % 1000003)} mod 2^64;
