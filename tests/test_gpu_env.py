@@ -255,3 +255,36 @@ def test_fused_env_skips_and_rejects(torch_cuda, ora):
     assert all(np.array_equal(before[k], after[k]) for k in before)
     with pytest.raises(ValueError):
         env.step(torch.full((N,), 1, dtype=torch.int32, device="cuda"))  # CHECK facing the blinds is invalid
+
+
+def test_env_phases_at_size_equal_the_single_launch(torch_cuda):
+    """PokerGameEnv.step on 2^17 four-player tables (thousands of stragglers per call, every phase populated) in phases
+    -- the default at this size -- and as ONE launch: rewards, done / hand flags, valid masks and the whole state are
+    identical after every call, resets of finished games included."""
+    torch = torch_cuda
+    from pokerl_b200.agents import RandomAgent
+    from pokerl_b200.envs import PokerGameEnv
+    N, T = (1 << 17) + 333, 14
+    envs = []
+    for phases in (True, False):
+        env = PokerGameEnv(agents=[RandomAgent() for _ in range(3)], num_envs=N, num_players=4, start_credits=60, big_blind=4,
+                           small_blind=2, seed=21, check_actions=False)
+        env.game.batch.set_env_phases(0 if phases else -1)
+        envs.append((env, env.reset()))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(T):
+        (ea, sa), (eb, sb) = envs
+        assert torch.equal(sa.valid_mask, sb.valid_mask), t
+        a = torch.multinomial(sa.valid_actions, 1, generator=gen)[:, 0].to(torch.int32)
+        sa, ra, da, ha = ea.step(a)
+        sb, rb, db, hb = eb.step(a)
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(da, db) and torch.equal(ha, hb), t
+        assert int(da.sum()) > 0 or t < 3
+        xa, xb = ea.game.batch.export(), eb.game.batch.export()
+        for k in xa:
+            assert np.array_equal(np.ascontiguousarray(xa[k]).view(np.uint8), np.ascontiguousarray(xb[k]).view(np.uint8)), (t, k)
+        if bool(da.any()):
+            sa, sb = ea.reset(env_mask=da), eb.reset(env_mask=db)
+        envs = [(ea, sa), (eb, sb)]
+    st_a, st_b = ea.game.batch.stats(), eb.game.batch.stats()
+    assert all(st_a[k] == st_b[k] for k in ("steps", "hands", "showdowns", "games", "invalid", "poisoned"))
